@@ -1,0 +1,77 @@
+"""ctypes binding of libvoxcarve.so — exactly the entry points include/voxcarve.h declares.
+
+There is no fallback: if the library is missing or was built without its kernels, loading
+raises, and every compute call needs a CUDA device (vc_create fails with VC_ERR_CUDA).
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libvoxcarve.so")
+
+VC_OK, VC_ERR_ARG, VC_ERR_CUDA, VC_ERR_STATE, VC_ERR_CAPACITY = 0, 1, 2, 3, 4
+VC_EXACT, VC_FAST_F32 = 0, 1
+VC_COLOR_CLOSEST, VC_COLOR_AVG = 1, 2
+VC_MASK_BITS, VC_MASK_BGR8 = 0, 1
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32), ("voxel_size", C.c_float),
+                ("z_begin", C.c_int32), ("z_end", C.c_int32), ("device", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("last_carve_ms", C.c_double), ("nominal_voxel_views", C.c_uint64),
+                ("executed_voxel_views", C.c_uint64), ("carve_launches", C.c_uint64),
+                ("l2_persist_bytes", C.c_uint64)]
+
+
+# name -> (restype, argtypes); the single source of truth the symbol-export test checks against the header
+_P = C.c_void_p
+SIGNATURES = {
+    "vc_create": (C.c_int, [C.POINTER(GridDesc), C.POINTER(_P)]),
+    "vc_destroy": (None, [_P]),
+    "vc_last_error": (C.c_char_p, [_P]),
+    "vc_api_version": (C.c_int, []),
+    "vc_set_stream": (C.c_int, [_P, _P]),
+    "vc_synchronize": (C.c_int, [_P]),
+    "vc_set_views": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "vc_set_masks": (C.c_int, [_P, _P, C.c_int32]),
+    "vc_set_images": (C.c_int, [_P, _P]),
+    "vc_reset": (C.c_int, [_P]),
+    "vc_carve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vc_fast_carve": (C.c_int, [_P, C.c_int32]),
+    "vc_color": (C.c_int, [_P, C.c_int32]),
+    "vc_mc_classify": (C.c_int, [_P]),
+    "vc_bind_volumes": (C.c_int, [_P, _P, _P]),
+    "vc_device_volumes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "vc_set_gathered": (C.c_int, [_P, C.c_int32]),
+    "vc_slab_words": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "vc_upload_volumes": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "vc_download_occupied": (C.c_int, [_P, _P, C.c_uint64]),
+    "vc_download_seen": (C.c_int, [_P, _P, C.c_uint64]),
+    "vc_count_occupied": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vc_surface_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "vc_download_colors": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "vc_download_mc": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "vc_measure_peaks": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libvoxcarve.so (must have been built: python -m ar_voxel_project_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -m ar_voxel_project_b200.build` "
+                               "(the engine has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,220 @@
+"""VoxelEngine — thin object wrapper over the C ABI (include/voxcarve.h).
+
+Host-side mirror of the reference's hot path: grid = Model(x, y, z, size) (Model.h:108), inputs =
+cached per-view P / M matrices and undistorted masks / images (VoxelCarving.cpp:25-36), outputs =
+bit-packed occupied / seen volumes, per-surface-voxel colours, cube-index histogram.
+All compute happens in libvoxcarve.so on the GPU; this file only marshals pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class VoxCarveError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"voxcarve error {code}: {msg}")
+        self.code = code
+
+
+def _host_ptr(a, dtype, nbytes_min, what):
+    """numpy array or CPU torch tensor -> (address, keepalive). Checks dtype, contiguity and size."""
+    if hasattr(a, "data_ptr"):  # torch tensor (e.g. pinned host memory)
+        if a.is_cuda:
+            raise ValueError(f"{what}: expected HOST memory")
+        if not a.is_contiguous():
+            raise ValueError(f"{what}: tensor must be contiguous")
+        nbytes = a.numel() * a.element_size()
+        if np.dtype(str(a.dtype).replace("torch.", "")) != np.dtype(dtype):
+            raise ValueError(f"{what}: dtype {a.dtype}, expected {np.dtype(dtype)}")
+        addr, keep = a.data_ptr(), a
+    else:
+        keep = np.ascontiguousarray(a, dtype=dtype)
+        nbytes, addr = keep.nbytes, keep.ctypes.data
+    if nbytes < nbytes_min:
+        raise ValueError(f"{what}: buffer has {nbytes} bytes, needs {nbytes_min}")
+    return addr, keep
+
+
+class VoxelEngine:
+    """One engine = one GPU = one z-slab [z_begin, z_end) of an X*Y*Z grid."""
+
+    def __init__(self, X, Y, Z, voxel_size, z_begin=0, z_end=None, device=0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        z_end = Z if z_end is None else z_end
+        g = L.GridDesc(int(X), int(Y), int(Z), float(np.float32(voxel_size)), int(z_begin), int(z_end), int(device))
+        rc = self._lib.vc_create(C.byref(g), C.byref(self._h))
+        if rc != L.VC_OK:
+            msg = self._lib.vc_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise VoxCarveError(rc, msg)
+        self.X, self.Y, self.Z, self.voxel_size = int(X), int(Y), int(Z), np.float32(voxel_size)
+        self.z_begin, self.z_end, self.device = int(z_begin), int(z_end), int(device)
+        self.Wx = (self.X + 31) // 32
+        self.V = self.W = self.H = 0
+        self._keep = []
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != L.VC_OK:
+            raise VoxCarveError(rc, self._lib.vc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.vc_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.vc_synchronize(self._h))
+
+    @property
+    def slab_shape(self):
+        return (self.z_end - self.z_begin, self.Y, self.Wx)
+
+    @property
+    def slab_words(self):
+        n = C.c_uint64()
+        self._check(self._lib.vc_slab_words(self._h, C.byref(n)))
+        return n.value
+
+    # -- inputs --------------------------------------------------------------------------
+    def set_views(self, P, W, H, M=None):
+        P = np.ascontiguousarray(P, np.float32).reshape(-1, 12)
+        V = P.shape[0]
+        Mp = None
+        if M is not None:
+            M = np.ascontiguousarray(M, np.float32).reshape(-1, 12)
+            if M.shape[0] != V:
+                raise ValueError("M and P must have the same number of views")
+            Mp = M.ctypes.data
+        self._check(self._lib.vc_set_views(self._h, V, int(W), int(H), P.ctypes.data, Mp))
+        self.V, self.W, self.H = V, int(W), int(H)
+
+    def set_masks_bits(self, bits):
+        """uint32[V][H][ceil(W/32)], 1 = background (carve)."""
+        need = self.V * self.H * ((self.W + 31) // 32) * 4
+        addr, keep = _host_ptr(bits, np.uint32, need, "mask bits")
+        self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BITS))
+        self.synchronize()  # host buffer may be pageable / temporary
+
+    def set_masks_bgr(self, bgr, sync=True):
+        """uint8[V][H][W][3] undistorted 8UC3 masks (VoxelCarving.cpp:36)."""
+        addr, keep = _host_ptr(bgr, np.uint8, self.V * self.H * self.W * 3, "mask bgr")
+        self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BGR8))
+        if sync:
+            self.synchronize()
+        else:
+            self._keep = [keep]
+
+    def set_masks_bits_async(self, bits):
+        need = self.V * self.H * ((self.W + 31) // 32) * 4
+        addr, keep = _host_ptr(bits, np.uint32, need, "mask bits")
+        self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BITS))
+        self._keep = [keep]
+
+    def set_images(self, images_bgr):
+        addr, keep = _host_ptr(images_bgr, np.uint8, self.V * self.H * self.W * 3, "images bgr")
+        self._check(self._lib.vc_set_images(self._h, C.c_void_p(addr)))
+        self.synchronize()
+
+    # -- hot path ------------------------------------------------------------------------
+    def reset(self):
+        self._check(self._lib.vc_reset(self._h))
+
+    def carve(self, mode=L.VC_EXACT, view_begin=0, view_end=-1, count_executed=False):
+        self._check(self._lib.vc_carve(self._h, mode, view_begin, view_end, int(bool(count_executed))))
+
+    def fast_carve(self, mode=L.VC_EXACT):
+        self._check(self._lib.vc_fast_carve(self._h, mode))
+
+    def color(self, mode):
+        self._check(self._lib.vc_color(self._h, int(mode)))
+
+    def mc_classify(self):
+        self._check(self._lib.vc_mc_classify(self._h))
+
+    # -- multi-GPU plumbing --------------------------------------------------------------
+    def bind_volumes(self, d_occ_full_ptr, d_seen_full_ptr):
+        self._check(self._lib.vc_bind_volumes(self._h, C.c_void_p(d_occ_full_ptr), C.c_void_p(d_seen_full_ptr)))
+
+    def device_volumes(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.vc_device_volumes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_gathered(self, flag=True):
+        self._check(self._lib.vc_set_gathered(self._h, int(bool(flag))))
+
+    def upload_volumes(self, occ_words, seen_words):
+        n = (self.z_end - self.z_begin) * self.Y * self.Wx
+        a, ka = _host_ptr(occ_words, np.uint32, n * 4, "occupied words")
+        b, kb = _host_ptr(seen_words, np.uint32, n * 4, "seen words")
+        self._check(self._lib.vc_upload_volumes(self._h, C.c_void_p(a), C.c_void_p(b), n))
+
+    # -- outputs -------------------------------------------------------------------------
+    def download_occupied(self, out=None):
+        return self._download(self._lib.vc_download_occupied, out)
+
+    def download_seen(self, out=None):
+        return self._download(self._lib.vc_download_seen, out)
+
+    def _download(self, fn, out):
+        n = (self.z_end - self.z_begin) * self.Y * self.Wx
+        if out is None:
+            out = np.empty(self.slab_shape, np.uint32)
+            addr = out.ctypes.data
+        else:
+            addr, _ = _host_ptr(out, np.uint32, n * 4, "download buffer")
+        self._check(fn(self._h, C.c_void_p(addr), n))
+        return out
+
+    def count_occupied(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.vc_count_occupied(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download_colors(self):
+        n = C.c_uint64()
+        self._check(self._lib.vc_surface_count(self._h, C.byref(n)))
+        idx = np.empty(n.value, np.uint64)
+        rgbn = np.empty((n.value, 4), np.uint8)
+        self._check(self._lib.vc_download_colors(self._h, C.c_void_p(idx.ctypes.data), C.c_void_p(rgbn.ctypes.data), n.value))
+        return idx, rgbn
+
+    def download_mc(self):
+        hist = np.zeros(256, np.uint64)
+        na, nt = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.vc_download_mc(self._h, C.c_void_p(hist.ctypes.data), C.byref(na), C.byref(nt)))
+        return hist, na.value, nt.value
+
+    def stats(self):
+        s = L.Stats()
+        self._check(self._lib.vc_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+
+def measure_peaks(device=0):
+    """Measured CUDA-core FFMA / DFMA peaks (TFLOP/s) of `device` — roofline denominators for bench.py."""
+    lib = L.load()
+    a, b = C.c_double(), C.c_double()
+    rc = lib.vc_measure_peaks(int(device), C.byref(a), C.byref(b))
+    if rc != L.VC_OK:
+        raise VoxCarveError(rc, lib.vc_last_error(None).decode())
+    return a.value, b.value

@@ -1,0 +1,152 @@
+/*
+ * voxcarve.h — C ABI of the B200-native voxel-carving engine (libvoxcarve.so).
+ *
+ * The reference (alxfox/AR_Voxel_Project) has no FFI layer: its hot path is four free
+ * functions on `Model&` called from main.cpp:260-303. This header is the boundary a thin
+ * C++ shim with those exact signatures binds to (include/voxcarve_shim.hpp).
+ * Each entry point names the reference interface it replaces (paths under src/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (VC_OK = 0); no exceptions cross the boundary; output buffers are caller-allocated;
+ * an engine is not thread-safe (the reference is single-threaded, Benchmark.h:59-63);
+ * all device memory is owned by the engine unless bound with vc_bind_volumes.
+ * There is NO CPU fallback: without a CUDA device every call fails with VC_ERR_CUDA.
+ *
+ * Device-resident grid layout (replaces Model::voxels alpha + Model::seen, Model.h:100-102):
+ *   word[(z*Y + y)*Wx + (x >> 5)], bit (x & 31), Wx = ceil(X/32); 1 = occupied / seen.
+ *   Row padding bits (x >= X) are always 0. z is the slowest index, as in Model::flatten
+ *   (Model.h:104-106), so a z-slab is one contiguous range and slabs gather in place.
+ */
+#ifndef VOXCARVE_H
+#define VOXCARVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_API_VERSION 1
+
+#if defined(__GNUC__)
+#define VC_EXPORT __attribute__((visibility("default")))
+#else
+#define VC_EXPORT
+#endif
+
+typedef struct vc_engine vc_engine; /* opaque */
+
+enum vc_status {
+    VC_OK = 0,
+    VC_ERR_ARG = 1,      /* bad argument (message in vc_last_error) */
+    VC_ERR_CUDA = 2,     /* CUDA runtime error, or no device */
+    VC_ERR_STATE = 3,    /* call order: views/masks/images not set, halo planes missing, ... */
+    VC_ERR_CAPACITY = 4  /* caller buffer too small */
+};
+
+/* Grid = Model(x, y, z, size) (Model.h:108, Model.cpp:9-14) restricted to the z-slab
+ * [z_begin, z_end) this engine carves. Single GPU: z_begin = 0, z_end = Z. */
+typedef struct vc_grid_desc {
+    int32_t X, Y, Z;
+    float voxel_size;
+    int32_t z_begin, z_end;
+    int32_t device; /* CUDA ordinal */
+} vc_grid_desc;
+
+/* Arithmetic of the projection (VoxelCarving.cpp:18-21).
+ * VC_EXACT reproduces the reference bit for bit: f32 world coords, f64 sequential
+ * accumulation of the 3x4.4x1 product rounded once to f32, IEEE f32 divides, round half away.
+ * It is built from explicit intrinsics, so nvcc's -fmad setting cannot change it.
+ * VC_FAST_F32 is a diagnostic f32/FMA pipeline (not bit-exact; see tests/test_fast_mode.py). */
+enum vc_carve_mode { VC_EXACT = 0, VC_FAST_F32 = 1 };
+/* values of the reference's -color flag (main.cpp:30,278-288) */
+enum vc_color_mode { VC_COLOR_CLOSEST = 1, VC_COLOR_AVG = 2 };
+enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1 };
+
+typedef struct vc_stats {
+    double last_carve_ms;          /* CUDA-event time of the last vc_carve (kernels only) */
+    uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
+    uint64_t executed_voxel_views; /* projections actually evaluated (0 unless counting was on) */
+    uint64_t carve_launches;       /* kernel launches issued by this engine so far */
+    uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
+} vc_stats;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+VC_EXPORT int vc_create(const vc_grid_desc* grid, vc_engine** out);
+VC_EXPORT void vc_destroy(vc_engine* e);
+/* message of the last failed call on `e`; with e == NULL, of the last failed vc_create */
+VC_EXPORT const char* vc_last_error(const vc_engine* e);
+VC_EXPORT int vc_api_version(void);
+/* run all work of this engine on a caller stream (cudaStream_t as void*; NULL = engine's own) */
+VC_EXPORT int vc_set_stream(vc_engine* e, void* cuda_stream);
+VC_EXPORT int vc_synchronize(vc_engine* e);
+
+/* ---- inputs ---------------------------------------------------------------------- */
+/* Per-view camera data, cached once per dataset (replaces the per-call
+ * estimatePoseFromImage + pose.inv() of VoxelCarving.cpp:25-30, ColorReconstruction.h:17-21):
+ *   P[v] = intr(CV_32F) * pose(3x4)  — first product of VoxelCarving.cpp:19, 12 f32 row-major
+ *   M[v] = pose(3x4) world->camera   — only its translation column is used (ColorReconstruction.h:21);
+ *          may be NULL if no colour pass is run. All pointers are HOST memory. */
+VC_EXPORT int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, const float* M);
+/* Undistorted silhouette masks (VoxelCarving.cpp:36). VC_MASK_BITS: uint32[V][H][ceil(W/32)],
+ * bit x&31 of word x>>5, 1 = background (pixel == (0,0,0), VoxelCarving.cpp:50).
+ * VC_MASK_BGR8: the 8UC3 images themselves, uint8[V][H][W][3]; packed on the device. HOST memory. */
+VC_EXPORT int vc_set_masks(vc_engine* e, const void* masks, int32_t format);
+/* Undistorted colour images 8UC3 BGR (ColorReconstruction.h:23), uint8[V][H][W][3], HOST memory. */
+VC_EXPORT int vc_set_images(vc_engine* e, const uint8_t* images_bgr);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+/* Model constructor state (Model.cpp:9-14): every voxel occupied, none seen. */
+VC_EXPORT int vc_reset(vc_engine* e);
+/* carve() (VoxelCarving.h:19, VoxelCarving.cpp:60-72) over views [view_begin, view_end) on this
+ * engine's slab; accumulates into the current volumes (call vc_reset first for a fresh Model).
+ * view_end < 0 means V. count_executed != 0 also fills vc_stats.executed_voxel_views (slower). */
+VC_EXPORT int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed);
+/* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): needs the whole grid on this engine. */
+VC_EXPORT int vc_fast_carve(vc_engine* e, int32_t mode);
+/* reconstructClosestColor / reconstructAvgColor (ColorReconstruction.h:131,142): colours every
+ * surface voxel (alpha != 0 && !isInner, ColorReconstruction.h:46) of this slab. */
+VC_EXPORT int vc_color(vc_engine* e, int32_t color_mode);
+/* Cube-index classification of marchingCubes() (MarchingCubes.cpp:12-18, MarchingCubes.h:479-488,
+ * :537-552) for the cells whose lower z-plane lies in this slab (plus z = -1 on the first slab). */
+VC_EXPORT int vc_mc_classify(vc_engine* e);
+
+/* ---- multi-GPU plumbing ---------------------------------------------------------- */
+/* Use caller-owned device buffers holding the WHOLE grid (Z*Y*Wx words each); the engine
+ * carves its slab in place at word offset z_begin*Y*Wx, so an all-gather of the slabs is in
+ * place, and colour / MC passes read neighbour planes from the gathered buffer. */
+VC_EXPORT int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full);
+/* device pointers of this engine's slab (first word of plane z_begin) */
+VC_EXPORT int vc_device_volumes(vc_engine* e, void** d_occupied_slab, void** d_seen_slab);
+/* declare that planes outside the slab held in a bound full volume are valid (after the gather) */
+VC_EXPORT int vc_set_gathered(vc_engine* e, int32_t gathered);
+
+/* ---- outputs (HOST buffers, caller-allocated) ------------------------------------ */
+VC_EXPORT int vc_slab_words(const vc_engine* e, uint64_t* n_words); /* (z_end-z_begin)*Y*Wx */
+/* Load this slab's volumes from HOST words: how the shim hands an existing Model (alpha != 0 and
+ * Model::seen, e.g. after applyClosure, main.cpp:297-303) to vc_color / vc_mc_classify. Padding
+ * bits are cleared. */
+VC_EXPORT int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* seen, uint64_t n_words);
+VC_EXPORT int vc_download_occupied(vc_engine* e, uint32_t* words, uint64_t n_words);
+VC_EXPORT int vc_download_seen(vc_engine* e, uint32_t* words, uint64_t n_words);
+VC_EXPORT int vc_count_occupied(vc_engine* e, uint64_t* n_occupied, uint64_t* n_seen);
+/* result of vc_color: one record per surface voxel in ascending flatten order
+ * (idx = x + X*(y + Y*z), Model.h:104-106); rgbn = r, g, b, min(#observations, 255);
+ * voxels with 0 observations keep MODEL_COLOR (ColorReconstruction.cpp:29-31, Model.h:90). */
+VC_EXPORT int vc_surface_count(vc_engine* e, uint64_t* n);
+VC_EXPORT int vc_download_colors(vc_engine* e, uint64_t* idx, uint8_t* rgbn, uint64_t capacity);
+/* result of vc_mc_classify: histogram of cube indices, #cells with edgeTable[idx] != 0,
+ * #triangles (sum of triTable row lengths / 3) */
+VC_EXPORT int vc_download_mc(vc_engine* e, uint64_t hist256[256], uint64_t* n_active, uint64_t* n_triangles);
+VC_EXPORT int vc_get_stats(vc_engine* e, vc_stats* out);
+
+/* ---- measurement helper (bench.py roofline denominators) ------------------------- */
+/* Register-resident FFMA and DFMA loops on `device`: measured CUDA-core peaks in TFLOP/s
+ * (2 flops per FMA), timed with CUDA events, best of 5. Not part of the carve path. */
+VC_EXPORT int vc_measure_peaks(int32_t device, double* ffma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXCARVE_H */

@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden fixtures.
+Bit-exact: occupancy / seen volumes, colour records, cube-index histograms."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A(lib_built):
+    import ar_voxel_project_b200 as A
+    return A
+
+
+def _carve(A, X, Y, Z, s, P, W, H, bits=None, bgr=None, M=None, z0=0, z1=None, mode=0, count=False):
+    with A.VoxelEngine(X, Y, Z, s, z_begin=z0, z_end=z1) as e:
+        e.set_views(P, W, H, M)
+        if bits is not None:
+            e.set_masks_bits(bits)
+        else:
+            e.set_masks_bgr(bgr)
+        e.carve(mode, count_executed=count)
+        return e.download_occupied(), e.download_seen(), e.stats()
+
+
+@pytest.mark.parametrize("ds", ["box", "human"])
+def test_carve_matches_literal_cv2_golden(A, oracle, golden, ds):
+    v, L = golden(f"{ds}_views.npz"), golden(f"{ds}_literal.npz")
+    X, Y, Z, s = int(L["X"]), int(L["Y"]), int(L["Z"]), L["s"]
+    occ, seen, _ = _carve(A, X, Y, Z, s, v["P"], int(v["W"]), int(v["H"]), bits=v["mask_bits"])
+    assert np.array_equal(oracle.unpack(occ, X), L["occ"])
+    assert np.array_equal(oracle.unpack(seen, X), L["seen"])
+
+
+@pytest.mark.parametrize("ds,dims", [("box", (100, 100, 100)), ("human", (100, 100, 100)), ("box", (100, 100, 50))])
+def test_carve_datasets_default_resolution(A, oracle, golden, ds, dims):
+    """BASELINE configs[0], [1]: box / human at the default 100^3, s = 0.0028 (main.cpp:26-29)"""
+    v = golden(f"{ds}_views.npz")
+    X, Y, Z = dims
+    s = np.float32(0.0028)
+    ro, rs = oracle.carve(X, Y, Z, s, v["P"], int(v["W"]), int(v["H"]), mask_bits=v["mask_bits"], nthreads=0)
+    occ, seen, st = _carve(A, X, Y, Z, s, v["P"], int(v["W"]), int(v["H"]), bits=v["mask_bits"], count=True)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+    assert 0 < st["executed_voxel_views"] <= st["nominal_voxel_views"] == X * Y * Z * int(v["V"])
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (5, 3, 2), (31, 7, 3), (32, 4, 4), (33, 5, 2), (127, 9, 3), (129, 2, 5), (200, 3, 3), (64, 64, 64)])
+def test_carve_ragged_grids_synthetic(A, oracle, dims):
+    """X not a multiple of 32 / 128, single voxel, thin grids: padding bits stay 0"""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = dims
+    w = Workload(max(dims), 7, 320, 200, seed=5, dims=dims)
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    occ, seen, _ = _carve(A, X, Y, Z, w.s, w.P, w.W, w.H, bits=w.mask_bits)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+    if X % 32:
+        assert (occ[..., -1] >> np.uint32(X % 32)).max() == 0 and (seen[..., -1] >> np.uint32(X % 32)).max() == 0
+
+
+def test_carve_bgr_masks_with_near_black_pixels(A, oracle, golden):
+    from ar_voxel_project_b200.synth import unpack_bits
+    v = golden("box_views.npz")
+    W, H = int(v["W"]), int(v["H"])
+    bg = unpack_bits(v["mask_bits"], W)
+    rng = np.random.default_rng(11)
+    bgr = rng.integers(0, 4, size=(*bg.shape, 3), dtype=np.uint8)
+    bgr[..., 1] |= 1  # foreground: never all-zero, but nearly black
+    bgr[bg] = 0
+    s = np.float32(0.0056)
+    ro, rs = oracle.carve(50, 50, 25, s, v["P"], W, H, mask_bgr=bgr)
+    occ, seen, _ = _carve(A, 50, 50, 25, s, v["P"], W, H, bgr=bgr)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+
+
+def test_carve_adversarial_cameras(A, oracle):
+    """behind-camera voxels still carve (no depth test, VoxelCarving.cpp:18-21); NaN/inf/zero-depth
+    projections are out of bounds; pixel-edge ties follow round-half-away."""
+    rng = np.random.default_rng(7)
+    W, H, X, Y, Z = 64, 48, 40, 12, 9
+    s = np.float32(0.25)
+    P = []
+    P.append(np.array([[0, 8, 0, 0.5], [0, 0, 8, 24.5], [0, 0, 0, 1]], np.float32))      # u = 8*x*s + .5 -> exact .5 ties
+    P.append(np.array([[0, 4, 0, -0.5], [4, 0, 0, 1.5], [0, 0, 0, 1]], np.float32))      # ties at -0.5 / .5
+    P.append(np.array([[30, 0, 0, 5], [0, 30, 0, 5], [0, 1, 0, -2.5]], np.float32))      # depth crosses zero inside the grid
+    P.append(np.array([[30, 0, 0, 5], [0, 30, 0, 5], [0, 0, 0, 0]], np.float32))         # depth == 0 -> inf / NaN
+    P.append(np.array([[np.nan, 0, 0, 5], [0, 30, 0, 5], [0, 0, 0, 1]], np.float32))     # NaN matrix
+    P.append(np.array([[1e38, 1e38, 0, 0], [0, 30, 0, 5], [0, 0, 1e-38, 1e-38]], np.float32))  # overflow / denormal depth
+    P.append(np.array([[-20, 3, 1, 30], [2, -25, 4, 40], [0.1, 0.2, -0.3, -1]], np.float32))   # camera behind: negative depth
+    for _ in range(6):
+        P.append((rng.standard_normal((3, 4)) * np.array([40, 40, 40, 20])).astype(np.float32))
+    P = np.stack(P)
+    bits = rng.integers(0, 2 ** 32, size=(len(P), H, (W + 31) // 32), dtype=np.uint64).astype(np.uint32)
+    for v0 in range(len(P)):  # one view at a time, so a disagreement names its view
+        ro, rs = oracle.carve(X, Y, Z, s, P[v0:v0 + 1], W, H, mask_bits=bits[v0:v0 + 1])
+        occ, seen, _ = _carve(A, X, Y, Z, s, P[v0:v0 + 1], W, H, bits=bits[v0:v0 + 1])
+        assert np.array_equal(occ, ro), f"occupied differs for adversarial view {v0}"
+        assert np.array_equal(seen, rs), f"seen differs for adversarial view {v0}"
+    ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits)
+    occ, seen, _ = _carve(A, X, Y, Z, s, P, W, H, bits=bits)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+
+
+def test_view_ranges_accumulate_and_carve_is_idempotent(A, golden):
+    """carving views one by one (the -intermediateMesh path, VoxelCarving.cpp:63-68) == one call; a
+    second pass changes nothing"""
+    v = golden("human_views.npz")
+    W, H, V = int(v["W"]), int(v["H"]), int(v["V"])
+    with A.VoxelEngine(100, 100, 60, 0.0028) as e:
+        e.set_views(v["P"], W, H)
+        e.set_masks_bits(v["mask_bits"])
+        e.carve()
+        occ, seen = e.download_occupied(), e.download_seen()
+        e.carve()
+        assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
+        e.reset()
+        for i in range(V):
+            e.carve(0, i, i + 1)
+        assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
+        n_occ, n_seen = e.count_occupied()
+        from ar_voxel_project_b200.synth import unpack_bits
+        assert n_occ == unpack_bits(occ, 100).sum() and n_seen == unpack_bits(seen, 100).sum()
+
+
+def test_z_slabs_tile_the_single_gpu_result(A, oracle):
+    from ar_voxel_project_b200.synth import Workload
+    w = Workload(96, 9, 320, 240, seed=2)
+    full = _carve(A, 96, 96, 96, w.s, w.P, w.W, w.H, bits=w.mask_bits)
+    for G in (2, 3, 8):
+        edges = [round(i * 96 / G) for i in range(G + 1)]
+        parts = [_carve(A, 96, 96, 96, w.s, w.P, w.W, w.H, bits=w.mask_bits, z0=a, z1=b) for a, b in zip(edges[:-1], edges[1:])]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+    ro, rs = oracle.carve(96, 96, 96, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=40, z1=44)
+    assert np.array_equal(full[0][40:44], ro) and np.array_equal(full[1][40:44], rs)
+
+
+def test_config3_512cubed_properties_and_oracle_slab(A, oracle):
+    """BASELINE configs[2] (512^3 x 36 views, 640x480) at full size: oracle on a 3-plane slab, plus
+    size-independent properties (carved => seen, padding, monotone in views, slab == whole)."""
+    from ar_voxel_project_b200.synth import Workload, CONFIGS, unpack_bits
+    w = Workload(**CONFIGS["C3"])
+    with A.VoxelEngine(512, 512, 512, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        e.carve(0, 0, 12)
+        occ12 = e.download_occupied()
+        e.carve(0, 12, -1)
+        occ, seen = e.download_occupied(), e.download_seen()
+    assert ((~occ) & (~seen)).max() == 0            # carved => seen
+    assert (occ & ~occ12).max() == 0                # more views never un-carve
+    frac = unpack_bits(occ[::8], 512).mean()
+    assert 0.01 < frac < 0.25, frac
+    for z0 in (0, 255, 509):
+        ro, rs = oracle.carve(512, 512, 512, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z0 + 3, nthreads=0)
+        assert np.array_equal(occ[z0:z0 + 3], ro) and np.array_equal(seen[z0:z0 + 3], rs)
+
+
+@pytest.mark.parametrize("ds", ["box", "human"])
+def test_colour_and_mc_match_literal_golden_and_oracle(A, oracle, golden, ds):
+    vs = A.ViewSet.from_npz(os.path.join(GOLDEN, f"{ds}_views.npz"))
+    L = golden(f"{ds}_literal.npz")
+    X, Y, Z, s = int(L["X"]), int(L["Y"]), int(L["Z"]), L["s"]
+    sf = L["surf"].astype(np.int64)
+    fl = sf[:, 0] + X * (sf[:, 1] + Y * sf[:, 2])
+    order = np.argsort(fl)
+    with A.VoxelEngine(X, Y, Z, s) as e:
+        e.set_views(vs.P, vs.W, vs.H, vs.M)
+        e.set_masks_bits(vs.mask_bits)
+        e.set_images(vs.images_bgr)
+        e.carve()
+        for mode, key in ((1, "closest"), (2, "avg")):
+            e.color(mode)
+            idx, rgbn = e.download_colors()
+            assert np.array_equal(idx, fl[order].astype(np.uint64))
+            assert np.array_equal(rgbn[:, :3], L[key][order])          # tolerance: 0/255 (north_star allows 1/255)
+            assert np.array_equal(rgbn[:, 3], np.minimum(L["nobs"][order], 255))
+        e.mc_classify()
+        hist, na, nt = e.download_mc()
+        occ = e.download_occupied()
+    rh, rna, rnt = oracle.mc_classify(X, Y, Z, occ)
+    assert np.array_equal(hist, rh) and (na, nt) == (rna, rnt)
+
+
+def test_config2_human_colour_default_resolution(A, oracle):
+    """BASELINE configs[1]: human_dataset carve + ColorReconstruction at 100^3"""
+    vs = A.ViewSet.from_npz(os.path.join(GOLDEN, "human_views.npz"))
+    s = np.float32(0.0028)
+    ro, _ = oracle.carve(100, 100, 100, s, vs.P, vs.W, vs.H, mask_bits=vs.mask_bits, nthreads=0)
+    with A.VoxelEngine(100, 100, 100, s) as e:
+        e.set_views(vs.P, vs.W, vs.H, vs.M)
+        e.set_masks_bits(vs.mask_bits)
+        e.set_images(vs.images_bgr)
+        e.carve()
+        assert np.array_equal(e.download_occupied(), ro)
+        for mode in (1, 2):
+            e.color(mode)
+            idx, rgbn = e.download_colors()
+            ridx, rrgbn = oracle.color(100, 100, 100, s, vs.P, vs.M, vs.W, vs.H, vs.images_bgr, ro, mode)
+            assert np.array_equal(idx, ridx)
+            assert np.abs(rgbn[:, :3].astype(int) - rrgbn[:, :3].astype(int)).max() <= 1   # north_star tolerance
+            assert np.array_equal(rgbn, rrgbn)                                              # and in fact exact
+        e.mc_classify()
+        hist, na, nt = e.download_mc()
+    rh, rna, rnt = oracle.mc_classify(100, 100, 100, ro)
+    assert np.array_equal(hist, rh) and (na, nt) == (rna, rnt)
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4), (31, 5, 7), (32, 6, 3), (33, 3, 3), (64, 9, 5), (95, 17, 11)])
+def test_mc_classify_random_volumes(A, oracle, dims):
+    """random occupancy incl. X = 31/32/33 (cell rows one longer than voxel rows)"""
+    from ar_voxel_project_b200.synth import pack_bits
+    X, Y, Z = dims
+    rng = np.random.default_rng(X * 131 + Y)
+    for p in (0.0, 0.5, 0.93, 1.0):
+        occ = pack_bits(rng.random((Z, Y, X)) < p)
+        with A.VoxelEngine(X, Y, Z, 1.0) as e:
+            e.upload_volumes(occ, occ)
+            e.mc_classify()
+            hist, na, nt = e.download_mc()
+        rh, rna, rnt = oracle.mc_classify(X, Y, Z, occ)
+        assert np.array_equal(hist, rh) and (na, nt) == (rna, rnt)
+        assert hist.sum() == (X + 1) * (Y + 1) * (Z + 1)
+
+
+def test_reference_named_api_on_model(A, oracle, golden):
+    """carve / reconstructAvgColor / marchingCubesClassify on a host Model, as main.cpp:260-303 calls them"""
+    vs = A.ViewSet.from_npz(os.path.join(GOLDEN, "box_views.npz"))
+    L = golden("box_literal.npz")
+    X, Y, Z, s = int(L["X"]), int(L["Y"]), int(L["Z"]), L["s"]
+    m = A.Model(X, Y, Z, s)
+    A.carve(vs, m)
+    assert np.array_equal(m.occupied_grid(), L["occ"])
+    assert np.array_equal(m.seen.reshape(Z, Y, X), L["seen"])
+    A.reconstructAvgColor(vs, m)
+    for (x, y, z), rgb, n in zip(L["surf"], L["avg"], L["nobs"]):
+        exp = rgb if n > 0 else (50, 168, 141)
+        assert tuple(m.get(x, y, z)[:3].astype(int)) == tuple(int(c) for c in exp)
+    m.handleUnseen()
+    hist, na, nt = A.marchingCubesClassify(m)
+    rh, rna, rnt = oracle.mc_classify(X, Y, Z, __import__("ar_voxel_project_b200.synth", fromlist=["pack_bits"]).pack_bits(m.occupied_grid()))
+    assert np.array_equal(hist, rh) and nt == rnt
+
+
+def test_errors_are_loud(A):
+    with pytest.raises(ValueError):
+        A.Model(0, 1, 1, 0.1)
+    with pytest.raises(A.VoxCarveError):
+        A.VoxelEngine(4, 4, 4, -1.0)
+    with A.VoxelEngine(4, 4, 4, 0.1) as e:
+        with pytest.raises(A.VoxCarveError):
+            e.carve()  # no views
+        e.set_views(np.zeros((2, 12), np.float32), 8, 8)
+        with pytest.raises(A.VoxCarveError):
+            e.carve()  # no masks
+        with pytest.raises(A.VoxCarveError):
+            e.color(2)  # no images
+    with A.VoxelEngine(4, 4, 8, 0.1, z_begin=2, z_end=4) as e:
+        with pytest.raises(A.VoxCarveError):
+            e.mc_classify()  # needs neighbour planes
