@@ -26,7 +26,8 @@ def _host_ptr(a, dtype, nbytes_min, what):
         if not a.is_contiguous():
             raise ValueError(f"{what}: tensor must be contiguous")
         nbytes = a.numel() * a.element_size()
-        if np.dtype(str(a.dtype).replace("torch.", "")) != np.dtype(dtype):
+        got = np.dtype(str(a.dtype).replace("torch.", ""))
+        if got.itemsize != np.dtype(dtype).itemsize or got.kind not in "iu":  # torch has no uint32 arithmetic: int32 is fine
             raise ValueError(f"{what}: dtype {a.dtype}, expected {np.dtype(dtype)}")
         addr, keep = a.data_ptr(), a
     else:

@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Minimal driver for ncu: set up one synthetic config, run reset+carve a few times (no torch)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import ar_voxel_project_b200 as A
+from ar_voxel_project_b200.synth import Workload, CONFIGS
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="C4")
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--mode", type=int, default=0)
+a = ap.parse_args()
+w = Workload(**CONFIGS[a.config])
+with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
+    e.set_views(w.P, w.W, w.H, w.M)
+    e.set_masks_bits(w.mask_bits)
+    for _ in range(a.reps):
+        e.reset()
+        e.carve(a.mode)
+        e.synchronize()
+        print("carve ms", e.stats()["last_carve_ms"])
+    e.reset()
+    e.carve(a.mode, count_executed=True)
+    st = e.stats()
+    print("executed", st["executed_voxel_views"], "nominal", st["nominal_voxel_views"], "occupied", e.count_occupied())
