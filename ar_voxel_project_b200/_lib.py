@@ -55,6 +55,7 @@ SIGNATURES = {
     "vc_download_colors": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "vc_download_mc": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "vc_selftest": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vc_measure_peaks": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

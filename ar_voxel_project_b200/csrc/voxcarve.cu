@@ -138,9 +138,9 @@ void set_mask_window(vc_engine* e, bool on) {
 
 template <int K>
 int launch_carve(vc_engine* e, int mode, const VcCarveParams& p, bool count) {
-    const long long blocks = (p.n_units + 3) / 4;
+    const long long blocks = (long long)p.G * p.YB * e->nz;
     if (blocks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld blocks)", blocks);
-    dim3 grid((unsigned)blocks), block(128);
+    dim3 grid((unsigned)blocks), block(32 * VC_TILE_ROWS);
     if (mode == VC_EXACT) {
         if (count) vc_carve_rows<K, true, true><<<grid, block, 0, e->stream>>>(p);
         else vc_carve_rows<K, true, false><<<grid, block, 0, e->stream>>>(p);
@@ -267,6 +267,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     }
     e->V = V; e->W = W; e->H = H; e->Ww = (W + 31) / 32;
     e->mask_bytes = (size_t)V * H * e->Ww * 4;
+    if (e->mask_bytes / 4 > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: %d views of %dx%d exceed 2^31 mask words", V, W, H);
     e->h_view.resize(V);
     e->h_cam.assign((size_t)V * 4, 0.0f);
     for (int v = 0; v < V; v++) {
@@ -344,12 +345,12 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     p.occ = e->occ_slab(); p.seen = e->seen_slab(); p.mask = e->d_mask;
     p.executed = e->d_scalars + 2;
     p.X = e->g.X; p.Y = e->g.Y; p.Wx = e->Wx; p.G = (e->Wx + K - 1) / K;
-    p.n_units = (long long)e->nz * e->g.Y * p.G;
+    p.YB = (e->g.Y + VC_TILE_ROWS - 1) / VC_TILE_ROWS;
     p.z_begin = e->g.z_begin;
     p.W = e->W; p.H = e->H; p.Ww = e->Ww;
     p.Wm05 = (float)e->W - 0.5f; p.Hm05 = (float)e->H - 0.5f;
     p.mask_plane = (uint32_t)((size_t)e->H * e->Ww);
-    p.v0 = view_begin; p.v1 = view_end; p.vbase = 0;
+    p.v0 = view_begin; p.v1 = view_end;
     p.s = e->g.voxel_size;
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
     set_mask_window(e, true);
@@ -611,6 +612,22 @@ int vc_measure_peaks(int32_t device, double* ffma_tflops, double* dfma_tflops) {
     if (s != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_measure_peaks: %s", cudaGetErrorString(s));
     *ffma_tflops = best[0];
     *dfma_tflops = best[1];
+    return VC_OK;
+}
+
+int vc_selftest(int32_t device, int32_t which, uint64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* checked) {
+    if (!mismatches || !checked || which < 0 || which > 1) return VC_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_selftest: cudaSetDevice(%d) failed", device);
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_selftest: cudaMalloc failed");
+    cudaMemset(d, 0, 16);
+    vc_selftest_kernel<<<148 * 8, 256>>>(which, n, seed, d, d + 1);
+    unsigned long long h[2] = {0, 0};
+    cudaError_t s = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (s != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_selftest: %s", cudaGetErrorString(s));
+    *mismatches = h[0];
+    *checked = h[1];
     return VC_OK;
 }
 

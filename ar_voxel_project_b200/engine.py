@@ -219,3 +219,13 @@ def measure_peaks(device=0):
     if rc != L.VC_OK:
         raise VoxCarveError(rc, lib.vc_last_error(None).decode())
     return a.value, b.value
+
+
+def selftest(which, n, seed=0, device=0):
+    """GPU self-test of the arithmetic shortcuts (0: shared-reciprocal divide, 1: pixel index). -> (mismatches, checked)"""
+    lib = L.load()
+    a, b = C.c_uint64(), C.c_uint64()
+    rc = lib.vc_selftest(int(device), int(which), int(n), int(seed), C.byref(a), C.byref(b))
+    if rc != L.VC_OK:
+        raise VoxCarveError(rc, lib.vc_last_error(None).decode())
+    return a.value, b.value

@@ -261,3 +261,12 @@ def test_errors_are_loud(A):
     with A.VoxelEngine(4, 4, 8, 0.1, z_begin=2, z_end=4) as e:
         with pytest.raises(A.VoxCarveError):
             e.mc_classify()  # needs neighbour planes
+
+
+def test_arithmetic_shortcuts_selftest(A):
+    """shared-reciprocal divide == IEEE div.rn (bitwise) and the 5-instruction pixel index == (int)roundf + inside(),
+    over 2 x 2^31 pseudo-random inputs incl. ties, edges, NaN/inf"""
+    from ar_voxel_project_b200.engine import selftest
+    for which in (0, 1):
+        bad, checked = selftest(which, 1 << 31, seed=12345 + which)
+        assert checked > (1 << 30) and bad == 0, (which, bad, checked)
