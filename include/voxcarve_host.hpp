@@ -1,0 +1,214 @@
+// voxcarve_host.hpp — header-only C++17 host layer over the C ABI (voxcarve.h).
+//
+// Mirrors the reference's free functions for the hot path, templated on the model type so that it
+// works with the reference's own `Model` (Model.h:93-163) unchanged and needs neither OpenCV nor
+// Eigen to compile:
+//     vc::carve / vc::fastCarve                          VoxelCarving.h:19,31
+//     vc::reconstructClosestColor / reconstructAvgColor   ColorReconstruction.h:131,142
+//     vc::marchingCubesClassify                           cube-index half of MarchingCubes.h:596
+// ModelT must offer what Model.h offers: getX(), getY(), getZ(), getSize(), get(x,y,z) returning a
+// 4-vector with operator()(int) and a (float,float,float,float) constructor, set(x,y,z,vec), see(x,y,z).
+// The per-dataset inputs the reference recomputes inside every call (estimatePoseFromImage +
+// cv::undistort, VoxelCarving.cpp:25,36; ColorReconstruction.h:17-28) arrive cached in a ViewCache;
+// voxcarve_shim.hpp builds one from (cameraMatrix, distCoeffs, images, masks) where OpenCV exists.
+// Errors: the reference prints to std::cerr and returns; this layer throws vc::Error (message from
+// vc_last_error) — nothing is ever computed on the CPU instead.
+#ifndef VOXCARVE_HOST_HPP
+#define VOXCARVE_HOST_HPP
+
+#include <cstdint>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "voxcarve.h"
+
+namespace vc {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("voxcarve error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+// Cached once per dataset.
+struct ViewCache {
+    int V = 0, W = 0, H = 0;
+    std::vector<float> P;             // V*12: intr(CV_32F) * pose(3x4), first product of VoxelCarving.cpp:19
+    std::vector<float> M;             // V*12: pose(3x4) world->camera (translation column = "camera", ColorReconstruction.h:21)
+    std::vector<uint32_t> mask_bits;  // V*H*ceil(W/32), 1 = background; or ...
+    std::vector<uint8_t> mask_bgr;    // ... V*H*W*3 undistorted 8UC3 masks (VoxelCarving.cpp:36)
+    std::vector<uint8_t> images_bgr;  // V*H*W*3 undistorted images (ColorReconstruction.h:23); empty if no colouring
+};
+
+struct McSummary {
+    uint64_t hist[256];
+    uint64_t active_cells, triangles;
+};
+
+class Engine {
+   public:
+    Engine(int X, int Y, int Z, float size, int z_begin = 0, int z_end = -1, int device = 0) : X_(X), Y_(Y), Z_(Z) {
+        vc_grid_desc g{X, Y, Z, size, z_begin, z_end < 0 ? Z : z_end, device};
+        int rc = vc_create(&g, &h_);
+        if (rc != VC_OK) throw Error(rc, vc_last_error(nullptr));
+        check(vc_slab_words(h_, &words_));
+    }
+    ~Engine() { vc_destroy(h_); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void setViews(const ViewCache& c, bool with_images) {
+        if ((int)c.P.size() != c.V * 12) throw Error(VC_ERR_ARG, "ViewCache.P must hold V*12 floats");
+        check(vc_set_views(h_, c.V, c.W, c.H, c.P.data(), c.M.empty() ? nullptr : c.M.data()));
+        if (!c.mask_bits.empty()) check(vc_set_masks(h_, c.mask_bits.data(), VC_MASK_BITS));
+        else if (!c.mask_bgr.empty()) check(vc_set_masks(h_, c.mask_bgr.data(), VC_MASK_BGR8));
+        if (with_images) {
+            if (c.images_bgr.empty()) throw Error(VC_ERR_ARG, "colour reconstruction needs ViewCache.images_bgr");
+            check(vc_set_images(h_, c.images_bgr.data()));
+        }
+        check(vc_synchronize(h_));  // the cache may be a temporary
+    }
+    void reset() { check(vc_reset(h_)); }
+    void carve(int mode = VC_EXACT, int v0 = 0, int v1 = -1) { check(vc_carve(h_, mode, v0, v1, 0)); }
+    void fastCarve(int mode = VC_EXACT) { check(vc_fast_carve(h_, mode)); }
+    void color(int mode) { check(vc_color(h_, mode)); }
+    McSummary mcClassify() {
+        McSummary s{};
+        check(vc_mc_classify(h_));
+        check(vc_download_mc(h_, s.hist, &s.active_cells, &s.triangles));
+        return s;
+    }
+    std::vector<uint32_t> occupied() { std::vector<uint32_t> w(words_); check(vc_download_occupied(h_, w.data(), words_)); return w; }
+    std::vector<uint32_t> seen() { std::vector<uint32_t> w(words_); check(vc_download_seen(h_, w.data(), words_)); return w; }
+    void upload(const std::vector<uint32_t>& occ, const std::vector<uint32_t>& seen) { check(vc_upload_volumes(h_, occ.data(), seen.data(), words_)); }
+    void colors(std::vector<uint64_t>& idx, std::vector<uint8_t>& rgbn) {
+        uint64_t n = 0;
+        check(vc_surface_count(h_, &n));
+        idx.resize(n);
+        rgbn.resize(n * 4);
+        check(vc_download_colors(h_, idx.data(), rgbn.data(), n));
+    }
+    vc_stats stats() { vc_stats s{}; check(vc_get_stats(h_, &s)); return s; }
+    vc_engine* handle() { return h_; }
+    int wordsPerRow() const { return (X_ + 31) / 32; }
+
+   private:
+    void check(int rc) { if (rc != VC_OK) throw Error(rc, vc_last_error(h_)); }
+    vc_engine* h_ = nullptr;
+    uint64_t words_ = 0;
+    int X_, Y_, Z_;
+};
+
+namespace detail {
+template <class ModelT>
+using Vec4Of = std::decay_t<decltype(std::declval<ModelT&>().get(0, 0, 0))>;
+
+// device bit volumes -> the reference Model: set(x,y,z,(0,0,0,0)) for carved voxels (VoxelCarving.cpp:52), see() (:54)
+template <class ModelT>
+void applyCarve(ModelT& model, const std::vector<uint32_t>& occ, const std::vector<uint32_t>& seen) {
+    const int X = model.getX(), Y = model.getY(), Z = model.getZ(), Wx = (X + 31) / 32;
+    const Vec4Of<ModelT> zero(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < Z; z++)
+        for (int y = 0; y < Y; y++)
+            for (int x = 0; x < X; x++) {
+                const size_t w = ((size_t)z * Y + y) * Wx + (x >> 5);
+                if (!((occ[w] >> (x & 31)) & 1u)) model.set(x, y, z, zero);
+                if ((seen[w] >> (x & 31)) & 1u) model.see(x, y, z);
+            }
+}
+
+// occupancy of an existing Model (alpha != 0) -> bit volume, for the colour / MC passes
+template <class ModelT>
+std::vector<uint32_t> packOccupancy(ModelT& model) {
+    const int X = model.getX(), Y = model.getY(), Z = model.getZ(), Wx = (X + 31) / 32;
+    std::vector<uint32_t> occ((size_t)Z * Y * Wx, 0u);
+    for (int z = 0; z < Z; z++)
+        for (int y = 0; y < Y; y++)
+            for (int x = 0; x < X; x++)
+                if (model.get(x, y, z)(3) != 0) occ[((size_t)z * Y + y) * Wx + (x >> 5)] |= 1u << (x & 31);
+    return occ;
+}
+
+template <class ModelT>
+void colorPass(const ViewCache& views, ModelT& model, int mode) {
+    Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
+    e.setViews(views, true);
+    const std::vector<uint32_t> occ = packOccupancy(model);
+    e.upload(occ, std::vector<uint32_t>(occ.size(), 0u));
+    e.color(mode);
+    std::vector<uint64_t> idx;
+    std::vector<uint8_t> rgbn;
+    e.colors(idx, rgbn);
+    const uint64_t X = model.getX(), Y = model.getY();
+    for (size_t i = 0; i < idx.size(); i++) {
+        if (rgbn[i * 4 + 3] == 0) continue;  // no observation: voxel untouched (ColorReconstruction.cpp:29-31)
+        const int x = (int)(idx[i] % X), y = (int)((idx[i] / X) % Y), z = (int)(idx[i] / (X * Y));
+        model.set(x, y, z, Vec4Of<ModelT>((float)rgbn[i * 4], (float)rgbn[i * 4 + 1], (float)rgbn[i * 4 + 2], 1.f));
+    }
+}
+}  // namespace detail
+
+// carve() — VoxelCarving.cpp:60-72. With intermediateMeshes, `perView` (if given) receives the cube-index
+// summary after every view, where the reference writes out/intermediate/image_<i>_mesh.off (:65-68).
+template <class ModelT>
+void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = false, std::vector<McSummary>* perView = nullptr) {
+    std::cout << "LOG - VC: starting carving process (version 1)." << std::endl;
+    Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
+    e.setViews(views, false);
+    if (intermediateMeshes) {
+        for (int i = 0; i < views.V; i++) {
+            e.carve(VC_EXACT, i, i + 1);
+            const McSummary s = e.mcClassify();
+            if (perView) perView->push_back(s);
+        }
+    } else {
+        e.carve();
+    }
+    detail::applyCarve(model, e.occupied(), e.seen());
+    std::cout << "LOG - VC: carving complete." << std::endl;
+}
+
+// fastCarve() — VoxelCarving.cpp:74-167
+template <class ModelT>
+void fastCarve(const ViewCache& views, ModelT& model) {
+    std::cout << "LOG - VC: starting carving process (version 2)." << std::endl;
+    Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
+    e.setViews(views, false);
+    e.fastCarve();
+    detail::applyCarve(model, e.occupied(), e.seen());
+    std::cout << "LOG - VC: carving complete." << std::endl;
+}
+
+// reconstructClosestColor() — ColorReconstruction.cpp:22-46
+template <class ModelT>
+void reconstructClosestColor(const ViewCache& views, ModelT& model) {
+    std::cout << "LOG - CR: starting color reconstruction (closest color)." << std::endl;
+    detail::colorPass(views, model, VC_COLOR_CLOSEST);
+    std::cout << "LOG - CR: color reconstruction finished." << std::endl;
+}
+
+// reconstructAvgColor() — ColorReconstruction.cpp:48-70
+template <class ModelT>
+void reconstructAvgColor(const ViewCache& views, ModelT& model) {
+    std::cout << "LOG - CR: starting color reconstruction (average color)." << std::endl;
+    detail::colorPass(views, model, VC_COLOR_AVG);
+    std::cout << "LOG - CR: color reconstruction finished." << std::endl;
+}
+
+// cube-index classification of marchingCubes() — MarchingCubes.cpp:12-18, MarchingCubes.h:479-488
+template <class ModelT>
+McSummary marchingCubesClassify(ModelT& model) {
+    std::cout << "LOG - MC: starting to process Voxels." << std::endl;
+    Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
+    const std::vector<uint32_t> occ = detail::packOccupancy(model);
+    e.upload(occ, std::vector<uint32_t>(occ.size(), 0u));
+    const McSummary s = e.mcClassify();
+    std::cout << "LOG - MC: voxel processing completed." << std::endl;
+    return s;
+}
+
+}  // namespace vc
+#endif  // VOXCARVE_HOST_HPP
