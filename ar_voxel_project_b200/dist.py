@@ -1,0 +1,44 @@
+"""z-slab sharding of the grid over the GPUs of one box.
+
+Voxels are independent, so each rank carves the contiguous slab z in [z0, z1) with every view; there
+is no exchange during carve.  When a consumer needs the whole bit-packed grid (marching cubes, the
+host Model), the slabs are assembled IN PLACE in a whole-grid buffer with one all-gather over
+NVLink (torch.distributed = plumbing; NCCL on GPUs, gloo in the CPU tests).  Reductions of the
+per-slab cube-index histograms / voxel counts are plain all-reduces.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_range(rank, world, Z):
+    """contiguous z-range of `rank`; sizes differ by at most one plane"""
+    return (rank * Z) // world, ((rank + 1) * Z) // world
+
+
+def all_gather_slabs(full, Z, world=None, group=None):
+    """full: tensor of shape (Z, ...) whose own slab is already filled in. Fills the other slabs in place."""
+    world = dist.get_world_size(group) if world is None else world
+    if world == 1:
+        return full
+    rank = dist.get_rank(group)
+    flat = full.view(Z, -1)
+    if Z % world == 0:
+        z0, z1 = slab_range(rank, world, Z)
+        dist.all_gather_into_tensor(flat.view(-1), flat[z0:z1].reshape(-1), group=group)
+    else:  # ragged slabs: one broadcast per owner
+        for r in range(world):
+            a, b = slab_range(r, world, Z)
+            if b > a:
+                dist.broadcast(flat[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return full
+
+
+def all_reduce_counts(values, device=None, group=None):
+    """sum of uint64 counters (histograms, voxel counts) over ranks -> numpy uint64"""
+    t = torch.from_numpy(np.ascontiguousarray(values, np.uint64).view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().view(np.uint64)

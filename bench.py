@@ -234,14 +234,14 @@ def run_ours(args):
 
     # on-demand assembly of the bit-packed grid (NCCL all-gather over NVLink), timed separately
     allgather_ms = None
-    if world > 1 and Z % world == 0:
-        plane = Y * Wx
+    if world > 1:
+        from ar_voxel_project_b200.dist import all_gather_slabs
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for it in range(3):
             barrier()
             g0.record()
-            dist.all_gather_into_tensor(occ_full.view(-1), occ_full.view(-1)[z0 * plane:z1 * plane])
-            dist.all_gather_into_tensor(seen_full.view(-1), seen_full.view(-1)[z0 * plane:z1 * plane])
+            all_gather_slabs(occ_full, Z, world)
+            all_gather_slabs(seen_full, Z, world)
             g1.record()
             torch.cuda.synchronize()
         allgather_ms = allmax(g0.elapsed_time(g1))

@@ -270,3 +270,48 @@ def test_arithmetic_shortcuts_selftest(A):
     for which in (0, 1):
         bad, checked = selftest(which, 1 << 31, seed=12345 + which)
         assert checked > (1 << 30) and bad == 0, (which, bad, checked)
+
+
+def test_bound_whole_grid_buffer_slabs_in_place(A, oracle):
+    """the multi-GPU data path on one GPU: two engines carve their z-slabs IN PLACE inside one caller-owned
+    whole-grid buffer (vc_bind_volumes); after that the 'gathered' buffer serves neighbour planes to the
+    colour and cube-index passes of both slabs, and the per-slab results add up to the whole-grid oracle."""
+    import torch
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 90, 40, 33
+    w = Workload(64, 6, 320, 240, seed=9, dims=(X, Y, Z))
+    Wx = (X + 31) // 32
+    occ_full = torch.zeros((Z, Y, Wx), dtype=torch.int32, device="cuda")
+    seen_full = torch.zeros_like(occ_full)
+    engines = []
+    for z0, z1 in ((0, 16), (16, Z)):
+        e = A.VoxelEngine(X, Y, Z, w.s, z_begin=z0, z_end=z1)
+        e.bind_volumes(occ_full.data_ptr(), seen_full.data_ptr())
+        e.set_views(w.P, w.W, w.H, w.M)
+        e.set_masks_bits(w.mask_bits)
+        e.set_images(w.images_bgr())
+        engines.append(e)
+    for e in engines:
+        e.carve()
+        e.synchronize()
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    assert np.array_equal(occ_full.cpu().numpy().view(np.uint32), ro)
+    assert np.array_equal(seen_full.cpu().numpy().view(np.uint32), rs)
+    with pytest.raises(A.VoxCarveError):
+        engines[1].mc_classify()  # neighbour planes not declared valid yet
+    hist = np.zeros(256, np.uint64)
+    idx_all, rgbn_all = [], []
+    for e in engines:
+        e.set_gathered(True)
+        e.mc_classify()
+        h, _, _ = e.download_mc()
+        hist += h
+        e.color(2)
+        i, c = e.download_colors()
+        idx_all.append(i), rgbn_all.append(c)
+    rh, rna, rnt = oracle.mc_classify(X, Y, Z, ro)
+    assert np.array_equal(hist, rh)
+    ridx, rrgbn = oracle.color(X, Y, Z, w.s, w.P, w.M, w.W, w.H, w.images_bgr(), ro, 2)
+    assert np.array_equal(np.concatenate(idx_all), ridx) and np.array_equal(np.concatenate(rgbn_all), rrgbn)
+    for e in engines:
+        e.close()
