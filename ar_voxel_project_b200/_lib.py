@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvoxcarve.so")
 
 VC_OK, VC_ERR_ARG, VC_ERR_CUDA, VC_ERR_STATE, VC_ERR_CAPACITY = 0, 1, 2, 3, 4
-VC_EXACT, VC_FAST_F32 = 0, 1
+VC_EXACT, VC_FAST_F32, VC_EXACT_FLAT = 0, 1, 2
 VC_COLOR_CLOSEST, VC_COLOR_AVG = 1, 2
 VC_MASK_BITS, VC_MASK_BGR8 = 0, 1
 
@@ -22,7 +22,7 @@ class GridDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("last_carve_ms", C.c_double), ("nominal_voxel_views", C.c_uint64),
-                ("executed_voxel_views", C.c_uint64), ("carve_launches", C.c_uint64),
+                ("executed_voxel_views", C.c_uint64), ("brick_corner_views", C.c_uint64), ("carve_launches", C.c_uint64),
                 ("l2_persist_bytes", C.c_uint64)]
 
 

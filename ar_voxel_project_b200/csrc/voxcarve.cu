@@ -44,6 +44,8 @@ struct vc_engine {
     std::vector<float> h_cam;
     bool have_M = false;
     uint32_t* d_mask = nullptr;
+    uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
+    VcBrickState* d_bricks = nullptr;    // one state per 32x8x8 brick of the slab
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
     // colour / mc results
@@ -225,6 +227,7 @@ void vc_destroy(vc_engine* e) {
     cudaSetDevice(e->g.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
+    cudaFree(e->d_sat); cudaFree(e->d_bricks);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist);
     free_color(e);
@@ -263,6 +266,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     if (V != e->V || W != e->W || H != e->H) {  // geometry changed: masks / images no longer match
         cudaFree(e->d_mask); e->d_mask = nullptr;
+        cudaFree(e->d_sat); e->d_sat = nullptr;
         cudaFree(e->d_images); e->d_images = nullptr;
     }
     e->V = V; e->W = W; e->H = H; e->Ww = (W + 31) / 32;
@@ -304,6 +308,16 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
         VC_CUDA(e, cudaGetLastError());
         VC_CUDA(e, cudaFreeAsync(d_tmp, e->stream));
     }
+    // summed-area tables for the brick classifier of VC_EXACT
+    const size_t sat_words = (size_t)e->V * (e->H + 1) * (e->W + 1);
+    if (!e->d_sat) VC_CUDA(e, cudaMalloc(&e->d_sat, sat_words * 4));
+    {
+        const long long n_rows = (long long)e->V * e->H;
+        vc_sat_rows_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, e->stream>>>(e->d_mask, e->d_sat, e->W, e->H, e->Ww, n_rows);
+        const long long n_cols = (long long)e->V * (e->W + 1);
+        vc_sat_cols_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, e->stream>>>(e->d_sat, e->W, e->H, e->V);
+        VC_CUDA(e, cudaGetLastError());
+    }
     return VC_OK;
 }
 
@@ -332,7 +346,7 @@ int vc_reset(vc_engine* e) {
 
 int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed) {
     if (!e) return VC_ERR_ARG;
-    if (mode != VC_EXACT && mode != VC_FAST_F32) return fail(e, VC_ERR_ARG, "vc_carve: unknown mode %d", mode);
+    if (mode != VC_EXACT && mode != VC_FAST_F32 && mode != VC_EXACT_FLAT) return fail(e, VC_ERR_ARG, "vc_carve: unknown mode %d", mode);
     if (e->V == 0 || !e->d_mask) return fail(e, VC_ERR_STATE, "vc_carve: views and masks must be set first");
     if (view_end < 0) view_end = e->V;
     if (view_begin < 0 || view_begin > view_end || view_end > e->V)
@@ -346,27 +360,49 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     p.executed = e->d_scalars + 2;
     p.X = e->g.X; p.Y = e->g.Y; p.Wx = e->Wx; p.G = (e->Wx + K - 1) / K;
     p.YB = (e->g.Y + VC_TILE_ROWS - 1) / VC_TILE_ROWS;
-    p.z_begin = e->g.z_begin;
+    p.z_begin = e->g.z_begin; p.nz = e->nz;
     p.W = e->W; p.H = e->H; p.Ww = e->Ww;
     p.Wm05 = (float)e->W - 0.5f; p.Hm05 = (float)e->H - 0.5f;
     p.mask_plane = (uint32_t)((size_t)e->H * e->Ww);
     p.v0 = view_begin; p.v1 = view_end;
     p.s = e->g.voxel_size;
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
+    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 5, 0, sizeof(unsigned long long), e->stream));
+    const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+    const long long n_bricks = (long long)nbx * nby * nbz;
+    if (mode == VC_EXACT) {
+        if (n_bricks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld bricks)", n_bricks);
+        if (!e->d_bricks) VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
+    }
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    rc = launch_carve<4>(e, mode, p, count_executed != 0);
-    if (rc) return rc;
+    if (mode == VC_EXACT) {
+        VcBrickParams bp{};
+        bp.state = e->d_bricks; bp.sat = e->d_sat; bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
+        bp.X = e->g.X; bp.Y = e->g.Y; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
+        bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
+        vc_brick_classify_kernel<<<(unsigned)((n_bricks + 127) / 128), 128, 0, e->stream>>>(bp);
+        if (count_executed) vc_carve_bricks<true><<<(unsigned)n_bricks, 512, 0, e->stream>>>(p, e->d_bricks, nbx, nby);
+        else vc_carve_bricks<false><<<(unsigned)n_bricks, 512, 0, e->stream>>>(p, e->d_bricks, nbx, nby);
+        VC_CUDA(e, cudaGetLastError());
+        e->stats.carve_launches += 2;
+    } else {
+        rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
+        if (rc) return rc;
+    }
     VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     set_mask_window(e, false);
     e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)(view_end - view_begin);
     e->stats.executed_voxel_views = 0;
+    e->stats.brick_corner_views = 0;
     e->stats.last_carve_ms = -1.0;  // resolved lazily in vc_get_stats
     if (count_executed) {
-        unsigned long long ex = 0;
+        unsigned long long ex = 0, bc = 0;
         VC_CUDA(e, cudaMemcpyAsync(&ex, e->d_scalars + 2, sizeof ex, cudaMemcpyDeviceToHost, e->stream));
+        VC_CUDA(e, cudaMemcpyAsync(&bc, e->d_scalars + 5, sizeof bc, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaStreamSynchronize(e->stream));
-        e->stats.executed_voxel_views = ex;
+        e->stats.executed_voxel_views = ex + (mode == VC_EXACT ? bc : 0);
+        e->stats.brick_corner_views = mode == VC_EXACT ? bc : 0;
     }
     e->gathered = false;
     e->have_colors = false;

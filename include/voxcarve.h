@@ -57,9 +57,12 @@ typedef struct vc_grid_desc {
 /* Arithmetic of the projection (VoxelCarving.cpp:18-21).
  * VC_EXACT reproduces the reference bit for bit: f32 world coords, f64 sequential
  * accumulation of the 3x4.4x1 product rounded once to f32, IEEE f32 divides, round half away.
- * It is built from explicit intrinsics, so nvcc's -fmad setting cannot change it.
+ * It is built from explicit intrinsics, so nvcc's -fmad setting cannot change it.  VC_EXACT classifies
+ * 32x8x8-voxel bricks per view first (conservatively, against a summed-area table of the silhouette)
+ * and evaluates only the undecided (brick, view) pairs per voxel; VC_EXACT_FLAT evaluates every
+ * voxel-view until its run is empty.  Both produce the same bits.
  * VC_FAST_F32 is a diagnostic f32/FMA pipeline (not bit-exact; see tests/test_fast_mode.py). */
-enum vc_carve_mode { VC_EXACT = 0, VC_FAST_F32 = 1 };
+enum vc_carve_mode { VC_EXACT = 0, VC_FAST_F32 = 1, VC_EXACT_FLAT = 2 };
 /* values of the reference's -color flag (main.cpp:30,278-288) */
 enum vc_color_mode { VC_COLOR_CLOSEST = 1, VC_COLOR_AVG = 2 };
 enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1 };
@@ -67,7 +70,8 @@ enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1 };
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (kernels only) */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
-    uint64_t executed_voxel_views; /* projections actually evaluated (0 unless counting was on) */
+    uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
+    uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
     uint64_t carve_launches;       /* kernel launches issued by this engine so far */
     uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
 } vc_stats;

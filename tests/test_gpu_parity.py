@@ -17,6 +17,7 @@ def A(lib_built):
 
 
 def _carve(A, X, Y, Z, s, P, W, H, bits=None, bgr=None, M=None, z0=0, z1=None, mode=0, count=False):
+    """carve with VC_EXACT (brick-classified) and check VC_EXACT_FLAT (every voxel-view) gives the same bits"""
     with A.VoxelEngine(X, Y, Z, s, z_begin=z0, z_end=z1) as e:
         e.set_views(P, W, H, M)
         if bits is not None:
@@ -24,7 +25,13 @@ def _carve(A, X, Y, Z, s, P, W, H, bits=None, bgr=None, M=None, z0=0, z1=None, m
         else:
             e.set_masks_bgr(bgr)
         e.carve(mode, count_executed=count)
-        return e.download_occupied(), e.download_seen(), e.stats()
+        out = e.download_occupied(), e.download_seen(), e.stats()
+        if mode == 0:
+            e.reset()
+            e.carve(2)
+            assert np.array_equal(e.download_occupied(), out[0]), "VC_EXACT and VC_EXACT_FLAT disagree (occupied)"
+            assert np.array_equal(e.download_seen(), out[1]), "VC_EXACT and VC_EXACT_FLAT disagree (seen)"
+        return out
 
 
 @pytest.mark.parametrize("ds", ["box", "human"])
@@ -46,6 +53,7 @@ def test_carve_datasets_default_resolution(A, oracle, golden, ds, dims):
     occ, seen, st = _carve(A, X, Y, Z, s, v["P"], int(v["W"]), int(v["H"]), bits=v["mask_bits"], count=True)
     assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
     assert 0 < st["executed_voxel_views"] <= st["nominal_voxel_views"] == X * Y * Z * int(v["V"])
+    assert 0 < st["brick_corner_views"] < st["executed_voxel_views"]
 
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (5, 3, 2), (31, 7, 3), (32, 4, 4), (33, 5, 2), (127, 9, 3), (129, 2, 5), (200, 3, 3), (64, 64, 64)])
@@ -150,6 +158,9 @@ def test_config3_512cubed_properties_and_oracle_slab(A, oracle):
         occ12 = e.download_occupied()
         e.carve(0, 12, -1)
         occ, seen = e.download_occupied(), e.download_seen()
+        e.reset()
+        e.carve(2)
+        assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
     assert ((~occ) & (~seen)).max() == 0            # carved => seen
     assert (occ & ~occ12).max() == 0                # more views never un-carve
     frac = unpack_bits(occ[::8], 512).mean()

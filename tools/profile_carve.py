@@ -25,4 +25,4 @@ with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
     e.reset()
     e.carve(a.mode, count_executed=True)
     st = e.stats()
-    print("executed", st["executed_voxel_views"], "nominal", st["nominal_voxel_views"], "occupied", e.count_occupied())
+    print("executed", st["executed_voxel_views"], "of which brick corners", st["brick_corner_views"], "nominal", st["nominal_voxel_views"], "occupied", e.count_occupied())
