@@ -45,7 +45,8 @@ struct vc_engine {
     bool have_M = false;
     uint32_t* d_mask = nullptr;
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
-    VcBrickState* d_bricks = nullptr;    // one state per 32x8x8 brick of the slab
+    VcBrickState* d_bricks = nullptr;    // work list: bricks of the slab that need per-voxel evaluation
+    int sm_count = 148;
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
     // colour / mc results
@@ -207,6 +208,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
         }                                                                                      \
     } while (0)
     VC_CREATE_CUDA(cudaSetDevice(g.device));
+    VC_CREATE_CUDA(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, g.device));
     VC_CREATE_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
@@ -377,13 +379,18 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     if (mode == VC_EXACT) {
+        unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length, [7] = work counter
+        unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
+        VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
         VcBrickParams bp{};
-        bp.state = e->d_bricks; bp.sat = e->d_sat; bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
-        bp.X = e->g.X; bp.Y = e->g.Y; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
+        bp.list = e->d_bricks; bp.n_list = d_nlist; bp.occ = p.occ; bp.seen = p.seen; bp.sat = e->d_sat;
+        bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
+        bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
         bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
-        vc_brick_classify_kernel<<<(unsigned)((n_bricks + 127) / 128), 128, 0, e->stream>>>(bp);
-        if (count_executed) vc_carve_bricks<true><<<(unsigned)n_bricks, 512, 0, e->stream>>>(p, e->d_bricks, nbx, nby);
-        else vc_carve_bricks<false><<<(unsigned)n_bricks, 512, 0, e->stream>>>(p, e->d_bricks, nbx, nby);
+        vc_brick_classify_kernel<<<(unsigned)((n_bricks * 8 + 255) / 256), 256, 0, e->stream>>>(bp);
+        const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
+        if (count_executed) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
+        else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         VC_CUDA(e, cudaGetLastError());
         e->stats.carve_launches += 2;
     } else {
