@@ -32,7 +32,8 @@ struct vc_engine {
     unsigned long long uid = 0;
     long long slab_words = 0, plane_words = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+    bool have_mid = false;
     // volumes
     uint32_t *d_occ_own = nullptr, *d_seen_own = nullptr;    // slab-sized, engine-owned
     uint32_t *d_occ_full = nullptr, *d_seen_full = nullptr;  // caller-owned whole grid (vc_bind_volumes)
@@ -213,6 +214,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     e->stream = e->own_stream;
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
     VC_CREATE_CUDA(cudaEventCreate(&e->ev1));
+    VC_CREATE_CUDA(cudaEventCreate(&e->evm));
     VC_CREATE_CUDA(cudaMalloc(&e->d_occ_own, e->slab_words * 4));
     VC_CREATE_CUDA(cudaMalloc(&e->d_seen_own, e->slab_words * 4));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 8 * sizeof(unsigned long long)));
@@ -235,6 +237,7 @@ void vc_destroy(vc_engine* e) {
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evm) cudaEventDestroy(e->evm);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     {
         std::lock_guard<std::mutex> lk(g_const_mutex);
@@ -378,6 +381,9 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     }
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    e->have_mid = mode == VC_EXACT;
+    e->stats.bricks_total = mode == VC_EXACT ? (uint64_t)n_bricks : 0;
+    e->stats.bricks_listed = 0;
     if (mode == VC_EXACT) {
         unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length, [7] = work counter
         unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
@@ -388,6 +394,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
         bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
         vc_brick_classify_kernel<<<(unsigned)((n_bricks * 8 + 255) / 256), 256, 0, e->stream>>>(bp);
+        VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
         const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
         if (count_executed) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
@@ -404,10 +411,12 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->stats.brick_corner_views = 0;
     e->stats.last_carve_ms = -1.0;  // resolved lazily in vc_get_stats
     if (count_executed) {
-        unsigned long long ex = 0, bc = 0;
+        unsigned long long ex = 0, bc = 0, nl = 0;
         VC_CUDA(e, cudaMemcpyAsync(&ex, e->d_scalars + 2, sizeof ex, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&bc, e->d_scalars + 5, sizeof bc, cudaMemcpyDeviceToHost, e->stream));
+        VC_CUDA(e, cudaMemcpyAsync(&nl, e->d_scalars + 6, sizeof nl, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaStreamSynchronize(e->stream));
+        e->stats.bricks_listed = mode == VC_EXACT ? (nl & 0xffffffffull) : 0;
         e->stats.executed_voxel_views = ex + (mode == VC_EXACT ? bc : 0);
         e->stats.brick_corner_views = mode == VC_EXACT ? bc : 0;
     }
@@ -620,6 +629,11 @@ int vc_get_stats(vc_engine* e, vc_stats* out) {
         float ms = 0.f;
         VC_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         e->stats.last_carve_ms = ms;
+        e->stats.last_classify_ms = 0.0;
+        if (e->have_mid) {
+            VC_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->evm));
+            e->stats.last_classify_ms = ms;
+        }
     }
     *out = e->stats;
     return VC_OK;

@@ -9,8 +9,9 @@ BASELINE.json quotes the metric on (default C4: 1024^3 x 72 views, 1920x1080 sil
 `value`  = X*Y*Z*V (nominal voxel-view projections of the job) / device time, masks resident in HBM.
 `e2e`    = same metric through the C ABI with HOST buffers: per step H2D of P/M + the 8UC3 masks from pinned
            memory, reset, carve, D2H of both bit volumes into pinned memory; wall clock, max over ranks.
-`roofline` = executed voxel-views (after the __all_sync early exits) * 23 FLOP / carve-kernel time against the
-           measured FFMA peak of this GPU (CUDA-core bound); `roofline_hbm` = grid-write bound.
+`roofline` = per-voxel projections executed by the dominant kernel (vc_carve_bricks: what is left after the brick
+           classification and the __all_sync early exits) * 23 FLOP / that kernel's time against the measured FFMA
+           peak of this GPU (CUDA-core bound); `roofline_hbm` = grid-write bound of the whole carve.
 `cpu_baseline` / --impl reference = oracle/ (C restatement of VoxelCarving.cpp:60-72) on a bounded z-slab sample.
 """
 import argparse
@@ -215,22 +216,37 @@ def run_ours(args):
     clk = clocks.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = allmax(float(np.mean(step_ms)))
-    launches = 2 * args.steps  # vc_reset_kernel + vc_carve_rows per step
+    launches = 3 * args.steps  # vc_reset_kernel + vc_brick_classify_kernel + vc_carve_bricks per step
 
     # carve-kernel-only time (events inside vc_carve) and executed voxel-views (separate, untimed counting pass)
-    kt = []
-    for _ in range(3):
+    kt, ct = [], []
+    for _ in range(5):
         flush.fill_(1)
         step()
-        kt.append(eng.stats()["last_carve_ms"])
+        st = eng.stats()
+        kt.append(st["last_carve_ms"]), ct.append(st["last_classify_ms"])
     kernel_ms = float(np.mean(kt))
+    classify_ms = float(np.mean(ct))
     eng.reset()
     eng.carve(A._lib.VC_EXACT, count_executed=True)
     st = eng.stats()
     executed_total = allsum(float(st["executed_voxel_views"]))
+    corner_total = allsum(float(st["brick_corner_views"]))
+    bricks_listed = allsum(float(st["bricks_listed"]))
+    bricks_total = allsum(float(st["bricks_total"]))
+    # the same job without brick classification (VC_EXACT_FLAT), for reference
+    flat = []
+    for _ in range(2):
+        flush.fill_(1)
+        eng.reset()
+        eng.carve(A._lib.VC_EXACT_FLAT)
+        flat.append(eng.stats()["last_carve_ms"])
+    flat_ms = allmax(float(flat[-1]))
     n_occ, n_seen = eng.count_occupied()
     occupied_total = allsum(float(n_occ))
     kernel_ms_max = allmax(kernel_ms)
+    fine_ms_max = allmax(kernel_ms - classify_ms)
+    classify_ms_max = allmax(classify_ms)
 
     # on-demand assembly of the bit-packed grid (NCCL all-gather over NVLink), timed separately
     allgather_ms = None
@@ -260,35 +276,46 @@ def run_ours(args):
     else:
         mc_tris = None
 
-    # end to end through the C ABI with host buffers
+    # end to end through the C ABI with host buffers: (a) the cached bit-packed silhouettes (SURVEY §7-1 cache format,
+    # what the CPU arm consumes too) and (b) the 8UC3 undistorted masks as the reference holds them in memory
     e2e = None
+    e2e_bgr = None
     if not args.no_e2e:
-        bgr = torch.from_numpy(w.mask_bgr()).pin_memory()
         out_occ = torch.empty((z1 - z0, Y, Wx), dtype=torch.int32).pin_memory()
         out_seen = torch.empty_like(out_occ).pin_memory()
-        h2d = bgr.numel() + w.P.nbytes + w.M.nbytes
         d2h = 2 * out_occ.numel() * 4
+        bits_pinned = torch.from_numpy(w.mask_bits.view(np.int32)).pin_memory()
+        bgr = torch.from_numpy(w.mask_bgr()).pin_memory()
 
-        def e2e_step():
-            eng.set_views(w.P, w.W, w.H, w.M)
-            eng.set_masks_bgr(bgr, sync=False)
-            eng.reset()
-            eng.carve(A._lib.VC_EXACT)
-            eng.download_occupied(out_occ)
-            eng.download_seen(out_seen)
+        def e2e_run(use_bits):
+            def one():
+                eng.set_views(w.P, w.W, w.H, w.M)
+                if use_bits:
+                    eng.set_masks_bits_async(bits_pinned)
+                else:
+                    eng.set_masks_bgr(bgr, sync=False)
+                eng.reset()
+                eng.carve(A._lib.VC_EXACT)
+                eng.download_occupied(out_occ)
+                eng.download_seen(out_seen)
+            for _ in range(2):
+                one()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                one()
+            barrier()
+            return allmax((time.perf_counter() - t0) / args.steps)
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        e2e_s = allmax((time.perf_counter() - t0) / args.steps)
-        launches_e2e = 3 * args.steps  # + vc_pack_bgr_kernel
-        e2e = {"value": nominal_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_s * 1e3, "mask_format": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device",
-               "gpu_launches": launches_e2e}
+        s_bits = e2e_run(True)
+        s_bgr = e2e_run(False)
+        # kernels per e2e step: [pack_bgr], sat_rows, sat_cols, reset, classify, carve_bricks
+        e2e = {"value": nominal_total / s_bits, "unit": UNIT, "h2d_bytes_per_step": int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bits * 1e3,
+               "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory", "gpu_launches": 5 * args.steps}
+        e2e_bgr = {"value": nominal_total / s_bgr, "unit": UNIT, "h2d_bytes_per_step": int(bgr.numel() + w.P.nbytes + w.M.nbytes),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bgr * 1e3,
+                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 6 * args.steps}
         eng.set_masks_bits(w.mask_bits)
 
     out = None
@@ -302,8 +329,9 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         kt_s = kernel_ms_max * 1e-3
-        exec_rank = executed_total / world  # per-launch average over ranks
-        ach = exec_rank * F_ALG / kt_s / 1e12
+        fine_s = fine_ms_max * 1e-3
+        exec_rank = (executed_total - corner_total) / world  # per-voxel projections of one vc_carve_bricks launch (rank average)
+        ach = exec_rank * F_ALG / fine_s / 1e12
         alg_bytes = 2.0 * (z1 - z0) * Y * Wx * 4 + w.mask_bits.nbytes
         out = {
             "metric": METRIC, "value": nominal_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -313,15 +341,18 @@ def run_ours(args):
             "executed_voxel_views": executed_total, "executed_fraction": executed_total / nominal_total,
             "executed_value": executed_total / (ms_per_step * 1e-3),
             "occupied_voxels": occupied_total, "carve_kernel_ms": kernel_ms_max,
+            "kernels_ms": {"vc_brick_classify_kernel": classify_ms_max, "vc_carve_bricks": fine_ms_max, "flat_vc_carve_rows_same_job": flat_ms},
+            "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma if ffma else None,
                          "traffic": None,
-                         "how": f"executed voxel-views per launch ({exec_rank:.4g}) x {F_ALG:.0f} FLOP / carve-kernel time; peak = FFMA "
-                                f"microbenchmark on this GPU (vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s"},
+                         "kernel": "vc_carve_bricks",
+                         "how": f"per-voxel projections of one vc_carve_bricks launch ({exec_rank:.4g}) x {F_ALG:.0f} FLOP / its time "
+                                f"({fine_ms_max:.3f} ms); peak = FFMA microbenchmark on this GPU (vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None,
                              "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}"},
             "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "e2e": e2e, "e2e_bgr8": e2e_bgr, "gpu_launches": launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference(w, args.cpu_seconds, 1, 1)

@@ -68,10 +68,13 @@ enum vc_color_mode { VC_COLOR_CLOSEST = 1, VC_COLOR_AVG = 2 };
 enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1 };
 
 typedef struct vc_stats {
-    double last_carve_ms;          /* CUDA-event time of the last vc_carve (kernels only) */
+    double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
+    double last_classify_ms;       /* of which: brick classification kernel (0 for the flat modes) */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
     uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
+    uint64_t bricks_total;         /* bricks of the slab / bricks that needed per-voxel work in the last VC_EXACT carve */
+    uint64_t bricks_listed;
     uint64_t carve_launches;       /* kernel launches issued by this engine so far */
     uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
 } vc_stats;
