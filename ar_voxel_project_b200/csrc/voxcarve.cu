@@ -42,11 +42,12 @@ struct vc_engine {
     int V = 0, W = 0, H = 0, Ww = 0;
     unsigned long long views_version = 0;
     std::vector<VcViewConst> h_view;
-    std::vector<float> h_cam;
+    std::vector<float> h_cam, h_absP;
     bool have_M = false;
     uint32_t* d_mask = nullptr;
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
     VcBrickState* d_bricks = nullptr;    // work list: bricks of the slab that need per-voxel evaluation
+    VcBrickState* d_super = nullptr;     // dense states of the super-bricks (level 1 of the classifier)
     int sm_count = 148;
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
@@ -98,6 +99,7 @@ int ensure_constants(vc_engine* e) {
     if (o.uid == e->uid && o.version == e->views_version) return VC_OK;
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_view, e->h_view.data(), sizeof(VcViewConst) * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_cam, e->h_cam.data(), sizeof(float) * 4 * e->V, 0, cudaMemcpyHostToDevice, e->stream));
+    VC_CUDA(e, cudaMemcpyToSymbolAsync(c_absP, e->h_absP.data(), sizeof(float) * 12 * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     // the host vectors may change right after this call returns; make the copy complete first
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     o.uid = e->uid;
@@ -231,7 +233,7 @@ void vc_destroy(vc_engine* e) {
     cudaSetDevice(e->g.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
-    cudaFree(e->d_sat); cudaFree(e->d_bricks);
+    cudaFree(e->d_sat); cudaFree(e->d_bricks); cudaFree(e->d_super);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist);
     free_color(e);
@@ -276,11 +278,14 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     }
     e->V = V; e->W = W; e->H = H; e->Ww = (W + 31) / 32;
     e->mask_bytes = (size_t)V * H * e->Ww * 4;
+    if ((unsigned long long)(W + 1) * (H + 1) > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: image %dx%d too large for 32-bit SAT offsets", W, H);
     if (e->mask_bytes / 4 > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: %d views of %dx%d exceed 2^31 mask words", V, W, H);
     e->h_view.resize(V);
     e->h_cam.assign((size_t)V * 4, 0.0f);
+    e->h_absP.assign((size_t)V * 12, 0.0f);
     for (int v = 0; v < V; v++) {
         for (int k = 0; k < 12; k++) e->h_view[v].P[k] = (double)P[v * 12 + k];
+        for (int k = 0; k < 12; k++) e->h_absP[v * 12 + k] = P[v * 12 + k] < 0 ? -P[v * 12 + k] : P[v * 12 + k];  // NaN stays NaN -> undecided
         if (M) {
             e->h_cam[v * 4 + 0] = M[v * 12 + 3];
             e->h_cam[v * 4 + 1] = M[v * 12 + 7];
@@ -379,6 +384,9 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         if (n_bricks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld bricks)", n_bricks);
         if (!e->d_bricks) VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
     }
+    const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
+    const long long n_super = (long long)sbx * sby * sbz;
+    if (mode == VC_EXACT && !e->d_super) VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     e->have_mid = mode == VC_EXACT;
@@ -393,13 +401,17 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
         bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
         bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
-        vc_brick_classify_kernel<<<(unsigned)((n_bricks * 8 + 255) / 256), 256, 0, e->stream>>>(bp);
+        VcBrickParams sp = bp;  // level 1: super-bricks into the dense array
+        sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
+        vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
+        bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
+        vc_brick_classify_kernel<0><<<(unsigned)((n_bricks * 8 + 255) / 256), 256, 0, e->stream>>>(bp);
         VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
         const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
         if (count_executed) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         VC_CUDA(e, cudaGetLastError());
-        e->stats.carve_launches += 2;
+        e->stats.carve_launches += 3;
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
         if (rc) return rc;
