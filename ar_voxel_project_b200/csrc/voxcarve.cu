@@ -48,6 +48,10 @@ struct vc_engine {
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
     VcBrickState* d_bricks = nullptr;    // work list: bricks of the slab that need per-voxel evaluation
     VcBrickState* d_super = nullptr;     // dense states of the super-bricks (level 1 of the classifier)
+    uint8_t* d_brick_flags = nullptr;    // VC_BRICK_* flags per brick
+    uint8_t* d_super_flags = nullptr;    // ... per super-brick
+    unsigned int* d_super_list = nullptr;
+    bool reset_pending = false;          // vc_reset not yet materialised (a VC_EXACT carve folds it into its fill pass)
     int sm_count = 148;
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
@@ -233,7 +237,7 @@ void vc_destroy(vc_engine* e) {
     cudaSetDevice(e->g.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
-    cudaFree(e->d_sat); cudaFree(e->d_bricks); cudaFree(e->d_super);
+    cudaFree(e->d_sat); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist);
     free_color(e);
@@ -342,12 +346,20 @@ int vc_set_images(vc_engine* e, const uint8_t* images_bgr) {
     return VC_OK;
 }
 
-int vc_reset(vc_engine* e) {
-    if (!e) return VC_ERR_ARG;
+// write the Model-constructor state now if a vc_reset is still pending (every reader / writer of the volumes calls this)
+static int materialize_reset(vc_engine* e) {
+    if (!e->reset_pending) return VC_OK;
     if (bind_device(e)) return VC_ERR_CUDA;
     const long long n = e->slab_words;
     vc_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), n, e->Wx, e->g.X);
     VC_CUDA(e, cudaGetLastError());
+    e->reset_pending = false;
+    return VC_OK;
+}
+
+int vc_reset(vc_engine* e) {
+    if (!e) return VC_ERR_ARG;
+    e->reset_pending = true;  // lazy: vc_carve(VC_EXACT) folds it into its coalesced fill pass
     e->gathered = false;
     e->have_colors = false;
     e->have_mc = false;
@@ -387,17 +399,24 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
     const long long n_super = (long long)sbx * sby * sbz;
     if (mode == VC_EXACT && !e->d_super) VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
+    if (mode == VC_EXACT && !e->d_brick_flags) {
+        VC_CUDA(e, cudaMalloc(&e->d_brick_flags, (size_t)n_bricks));
+        VC_CUDA(e, cudaMalloc(&e->d_super_flags, (size_t)n_super));
+        VC_CUDA(e, cudaMalloc(&e->d_super_list, (size_t)n_super * sizeof(unsigned int)));
+    }
+    if (mode != VC_EXACT) { rc = materialize_reset(e); if (rc) return rc; }
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     e->have_mid = mode == VC_EXACT;
     e->stats.bricks_total = mode == VC_EXACT ? (uint64_t)n_bricks : 0;
     e->stats.bricks_listed = 0;
     if (mode == VC_EXACT) {
-        unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length, [7] = work counter
+        unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length | super-list length, [7] = work counter
         unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
         VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
         VcBrickParams bp{};
-        bp.list = e->d_bricks; bp.n_list = d_nlist; bp.occ = p.occ; bp.seen = p.seen; bp.sat = e->d_sat;
+        bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
+        bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
         bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
         bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
         bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
@@ -405,13 +424,17 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
         vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
         bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-        vc_brick_classify_kernel<0><<<(unsigned)((n_bricks * 8 + 255) / 256), 256, 0, e->stream>>>(bp);
+        vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
+        const unsigned n_rows = (unsigned)((long long)e->nz * e->g.Y);
+        vc_fill_kernel<<<dim3((n_rows + 7) / 8, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
+            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, n_rows, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, e->reset_pending ? 1 : 0);
+        e->reset_pending = false;
         VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
         const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
         if (count_executed) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
         VC_CUDA(e, cudaGetLastError());
-        e->stats.carve_launches += 3;
+        e->stats.carve_launches += 4;
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
         if (rc) return rc;
@@ -457,6 +480,7 @@ int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full) {
 
 int vc_device_volumes(vc_engine* e, void** d_occupied_slab, void** d_seen_slab) {
     if (!e || !d_occupied_slab || !d_seen_slab) return VC_ERR_ARG;
+    if (materialize_reset(e)) return VC_ERR_CUDA;
     *d_occupied_slab = e->occ_slab();
     *d_seen_slab = e->seen_slab();
     return VC_OK;
@@ -464,6 +488,7 @@ int vc_device_volumes(vc_engine* e, void** d_occupied_slab, void** d_seen_slab) 
 
 int vc_set_gathered(vc_engine* e, int32_t gathered) {
     if (!e) return VC_ERR_ARG;
+    if (materialize_reset(e)) return VC_ERR_CUDA;
     if (gathered && !e->d_occ_full) return fail(e, VC_ERR_STATE, "vc_set_gathered: no full volume bound");
     e->gathered = gathered != 0;
     return VC_OK;
@@ -480,6 +505,7 @@ int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* se
     if (!occupied || !seen) return fail(e, VC_ERR_ARG, "vc_upload_volumes: null buffer");
     if (n_words != (uint64_t)e->slab_words) return fail(e, VC_ERR_ARG, "vc_upload_volumes: got %llu words, slab has %lld", (unsigned long long)n_words, e->slab_words);
     if (bind_device(e)) return VC_ERR_CUDA;
+    e->reset_pending = false;  // overwritten entirely
     VC_CUDA(e, cudaMemcpyAsync(e->occ_slab(), occupied, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyAsync(e->seen_slab(), seen, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     vc_clear_padding_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), e->slab_words, e->Wx, e->g.X);
@@ -493,6 +519,7 @@ static int download_words(vc_engine* e, const uint32_t* d, uint32_t* words, uint
     if (!words) return fail(e, VC_ERR_ARG, "download: null buffer");
     if (n_words < (uint64_t)e->slab_words) return fail(e, VC_ERR_CAPACITY, "download: buffer holds %llu words, slab has %lld", (unsigned long long)n_words, e->slab_words);
     if (bind_device(e)) return VC_ERR_CUDA;
+    if (materialize_reset(e)) return VC_ERR_CUDA;
     VC_CUDA(e, cudaMemcpyAsync(words, d, e->slab_words * 4, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     return VC_OK;
@@ -503,6 +530,7 @@ int vc_download_seen(vc_engine* e, uint32_t* words, uint64_t n_words) { return e
 int vc_count_occupied(vc_engine* e, uint64_t* n_occupied, uint64_t* n_seen) {
     if (!e || !n_occupied || !n_seen) return VC_ERR_ARG;
     if (bind_device(e)) return VC_ERR_CUDA;
+    if (materialize_reset(e)) return VC_ERR_CUDA;
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 3, 0, 2 * sizeof(unsigned long long), e->stream));
     vc_popcount_kernel<<<148 * 8, 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), e->slab_words, e->d_scalars + 3);
     VC_CUDA(e, cudaGetLastError());
@@ -529,6 +557,8 @@ int vc_color(vc_engine* e, int32_t color_mode) {
     int rc = need_halo(e, "vc_color");
     if (rc) return rc;
     if (bind_device(e)) return VC_ERR_CUDA;
+    rc = materialize_reset(e);
+    if (rc) return rc;
     rc = ensure_constants(e);
     if (rc) return rc;
     const long long n = e->slab_words;
@@ -599,6 +629,8 @@ int vc_mc_classify(vc_engine* e) {
     int rc = need_halo(e, "vc_mc_classify");
     if (rc) return rc;
     if (bind_device(e)) return VC_ERR_CUDA;
+    rc = materialize_reset(e);
+    if (rc) return rc;
     // cells whose lower plane z is in [z_begin, z_end), plus z = -1 on the first slab (MarchingCubes.cpp:14)
     const int cz_begin = e->g.z_begin == 0 ? -1 : e->g.z_begin;
     const int n_cz = e->g.z_end - cz_begin;
