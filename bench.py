@@ -199,10 +199,11 @@ def run_ours(args):
         eng.reset()
         eng.carve(A._lib.VC_EXACT)
 
+    clocks = ClockSampler(local)  # spans warm-up, the timed steps and an identical untimed tail (nvidia-smi period: 100 ms)
+    t_clk = time.perf_counter()
     for _ in range(args.warmup):
         flush.fill_(1)
         step()
-    clocks = ClockSampler(local)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
@@ -213,7 +214,14 @@ def run_ours(args):
         b.record()
         kernel_ms.append(None)
     barrier()
+    n_tail = 0
+    while time.perf_counter() - t_clk < 2.0:  # keep the same load up until the sampler has ~20 samples
+        flush.fill_(1)
+        step()
+        n_tail += 1
+    torch.cuda.synchronize()
     clk = clocks.stop()
+    clk["sampled_over"] = f"{args.warmup} warm-up + {args.steps} timed + {n_tail} identical untimed steps"
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = allmax(float(np.mean(step_ms)))
     launches = 3 * args.steps  # vc_reset_kernel + vc_brick_classify_kernel + vc_carve_bricks per step
@@ -328,6 +336,14 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{args.config}_x{world}"
+            if key in tr:
+                traffic = tr[key]["vc_carve_bricks_dram_bytes"]
+        except Exception:
+            pass
         kt_s = kernel_ms_max * 1e-3
         fine_s = fine_ms_max * 1e-3
         exec_rank = (executed_total - corner_total) / world  # per-voxel projections of one vc_carve_bricks launch (rank average)
@@ -344,7 +360,7 @@ def run_ours(args):
             "kernels_ms": {"vc_brick_classify_kernel": classify_ms_max, "vc_carve_bricks": fine_ms_max, "flat_vc_carve_rows_same_job": flat_ms},
             "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma if ffma else None,
-                         "traffic": None,
+                         "traffic": traffic, "algorithmic_bytes": exec_rank / 8.0 + 2.0 * bricks_listed / world * 2048 / 8,
                          "kernel": "vc_carve_bricks",
                          "how": f"per-voxel projections of one vc_carve_bricks launch ({exec_rank:.4g}) x {F_ALG:.0f} FLOP / its time "
                                 f"({fine_ms_max:.3f} ms); peak = FFMA microbenchmark on this GPU (vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s"},
