@@ -46,6 +46,9 @@ struct vc_engine {
     bool have_M = false;
     uint32_t* d_mask = nullptr;
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
+    uint32_t* d_sat_tmp = nullptr;       // V x H x Ww word-column prefixes used while building d_sat
+    uint8_t* d_bgr_tmp = nullptr;        // staging for 8UC3 masks (grow-only)
+    size_t bgr_tmp_bytes = 0;
     VcBrickState* d_bricks = nullptr;    // work list: bricks of the slab that need per-voxel evaluation
     VcBrickState* d_super = nullptr;     // dense states of the super-bricks (level 1 of the classifier)
     uint8_t* d_brick_flags = nullptr;    // VC_BRICK_* flags per brick
@@ -237,7 +240,7 @@ void vc_destroy(vc_engine* e) {
     cudaSetDevice(e->g.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
-    cudaFree(e->d_sat); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
+    cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist);
     free_color(e);
@@ -278,6 +281,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     if (V != e->V || W != e->W || H != e->H) {  // geometry changed: masks / images no longer match
         cudaFree(e->d_mask); e->d_mask = nullptr;
         cudaFree(e->d_sat); e->d_sat = nullptr;
+        cudaFree(e->d_sat_tmp); e->d_sat_tmp = nullptr;
         cudaFree(e->d_images); e->d_images = nullptr;
     }
     e->V = V; e->W = W; e->H = H; e->Ww = (W + 31) / 32;
@@ -313,23 +317,29 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
         VC_CUDA(e, cudaMemcpyAsync(e->d_mask, masks, e->mask_bytes, cudaMemcpyHostToDevice, e->stream));
     } else {
         const size_t bytes = (size_t)e->V * e->H * e->W * 3;
-        uint8_t* d_tmp = nullptr;
-        VC_CUDA(e, cudaMallocAsync(&d_tmp, bytes, e->stream));
+        if (e->bgr_tmp_bytes < bytes) {
+            VC_CUDA(e, cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_bgr_tmp); e->d_bgr_tmp = nullptr; e->bgr_tmp_bytes = 0;
+            VC_CUDA(e, cudaMalloc(&e->d_bgr_tmp, bytes));
+            e->bgr_tmp_bytes = bytes;
+        }
+        uint8_t* d_tmp = e->d_bgr_tmp;
         VC_CUDA(e, cudaMemcpyAsync(d_tmp, masks, bytes, cudaMemcpyHostToDevice, e->stream));
         const long long n_rows = (long long)e->V * e->H, warps = n_rows * e->Ww;
         const long long blocks = (warps * 32 + 255) / 256;
         vc_pack_bgr_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(d_tmp, e->d_mask, e->W, e->Ww, n_rows);
         VC_CUDA(e, cudaGetLastError());
-        VC_CUDA(e, cudaFreeAsync(d_tmp, e->stream));
     }
     // summed-area tables for the brick classifier of VC_EXACT
     const size_t sat_words = (size_t)e->V * (e->H + 1) * (e->W + 1);
     if (!e->d_sat) VC_CUDA(e, cudaMalloc(&e->d_sat, sat_words * 4));
+    if (!e->d_sat_tmp) VC_CUDA(e, cudaMalloc(&e->d_sat_tmp, e->mask_bytes));
     {
         const long long n_rows = (long long)e->V * e->H;
-        vc_sat_rows_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, e->stream>>>(e->d_mask, e->d_sat, e->W, e->H, e->Ww, n_rows);
-        const long long n_cols = (long long)e->V * (e->W + 1);
-        vc_sat_cols_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, e->stream>>>(e->d_sat, e->W, e->H, e->V);
+        const int n_cols = e->V * e->Ww;
+        vc_sat_rowprefix_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(e->d_mask, e->d_sat_tmp, e->Ww, n_rows);
+        vc_sat_coldown_kernel<<<(n_cols + 63) / 64, 64, 0, e->stream>>>(e->d_sat_tmp, e->Ww, e->H, e->V);
+        vc_sat_expand_kernel<<<(n_cols * 32 + 255) / 256, 256, 0, e->stream>>>(e->d_mask, e->d_sat_tmp, e->d_sat, e->W, e->H, e->Ww, e->V);
         VC_CUDA(e, cudaGetLastError());
     }
     return VC_OK;
