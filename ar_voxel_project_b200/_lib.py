@@ -23,7 +23,7 @@ class GridDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("last_carve_ms", C.c_double), ("last_classify_ms", C.c_double), ("nominal_voxel_views", C.c_uint64),
                 ("executed_voxel_views", C.c_uint64), ("brick_corner_views", C.c_uint64),
-                ("bricks_total", C.c_uint64), ("bricks_listed", C.c_uint64), ("carve_launches", C.c_uint64),
+                ("bricks_total", C.c_uint64), ("bricks_listed", C.c_uint64), ("flood_rounds", C.c_uint64), ("carve_launches", C.c_uint64),
                 ("l2_persist_bytes", C.c_uint64)]
 
 

@@ -472,9 +472,44 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
 }
 
 int vc_fast_carve(vc_engine* e, int32_t mode) {
-    (void)mode;
     if (!e) return VC_ERR_ARG;
-    return fail(e, VC_ERR_STATE, "vc_fast_carve: not built yet (SURVEY 8f-3)");
+    if (!e->whole_grid()) return fail(e, VC_ERR_STATE, "vc_fast_carve: the flood from voxel (0,0,0) needs the whole grid on one engine (slab [%d,%d) of Z=%d)", e->g.z_begin, e->g.z_end, e->g.Z);
+    // the set carve() would carve, on a fresh Model (fastCarve starts from the constructor state, main.cpp:248-264)
+    int rc = vc_reset(e);
+    if (rc) return rc;
+    rc = vc_carve(e, mode, 0, -1, 0);
+    if (rc) return rc;
+    const long long n = e->slab_words;
+    uint32_t* F = nullptr;
+    int* d_changed = nullptr;
+    VC_CUDA(e, cudaMalloc(&F, n * 4 + 16));
+    d_changed = (int*)(F + n);
+    VC_CUDA(e, cudaMemsetAsync(F, 0, n * 4 + 16, e->stream));
+    uint32_t *occ = e->occ_slab(), *seen = e->seen_slab();
+    const int X = e->g.X, Y = e->g.Y, Z = e->g.Z, Wx = e->Wx;
+    vc_flood_seed_kernel<<<1, 1, 0, e->stream>>>(occ, F);
+    const long long n_rows = (long long)Y * Z;
+    int rounds = 0;
+    for (;; rounds++) {
+        if (rounds > 100000) { cudaFree(F); return fail(e, VC_ERR_STATE, "vc_fast_carve: flood did not converge"); }
+        cudaMemsetAsync(d_changed, 0, sizeof(int), e->stream);
+        vc_flood_x_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, n_rows, X, d_changed);
+        // along y: one thread per (z, word column); along z: one thread per (y, word column)
+        vc_flood_axis_kernel<<<(unsigned)(((long long)Z * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Y, Wx, (long long)Y * Wx, Z, d_changed);
+        vc_flood_axis_kernel<<<(unsigned)(((long long)Y * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Z, (long long)Y * Wx, Wx, Y, d_changed);
+        int h = 0;
+        cudaError_t s = cudaMemcpyAsync(&h, d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+        if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
+        if (s != cudaSuccess) { cudaFree(F); return fail(e, VC_ERR_CUDA, "vc_fast_carve: %s", cudaGetErrorString(s)); }
+        if (!h) break;
+    }
+    vc_flood_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(F, occ, seen, X, Y, Z, Wx);
+    cudaError_t s = cudaGetLastError();
+    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
+    cudaFree(F);
+    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_fast_carve: %s", cudaGetErrorString(s));
+    e->stats.flood_rounds = (uint64_t)rounds + 1;
+    return VC_OK;
 }
 
 int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full) {

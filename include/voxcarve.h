@@ -75,6 +75,7 @@ typedef struct vc_stats {
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
     uint64_t bricks_total;         /* bricks of the slab / bricks that needed per-voxel work in the last VC_EXACT carve */
     uint64_t bricks_listed;
+    uint64_t flood_rounds;         /* sweep rounds of the last vc_fast_carve */
     uint64_t carve_launches;       /* kernel launches issued by this engine so far */
     uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
 } vc_stats;
@@ -110,7 +111,8 @@ VC_EXPORT int vc_reset(vc_engine* e);
  * engine's slab; accumulates into the current volumes (call vc_reset first for a fresh Model).
  * view_end < 0 means V. count_executed != 0 also fills vc_stats.executed_voxel_views (slower). */
 VC_EXPORT int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed);
-/* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): needs the whole grid on this engine. */
+/* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): starts from the Model constructor state (it resets the
+ * volumes itself) and needs the whole grid on this engine. */
 VC_EXPORT int vc_fast_carve(vc_engine* e, int32_t mode);
 /* reconstructClosestColor / reconstructAvgColor (ColorReconstruction.h:131,142): colours every
  * surface voxel (alpha != 0 && !isInner, ColorReconstruction.h:46) of this slab. */

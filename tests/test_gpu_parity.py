@@ -326,3 +326,37 @@ def test_bound_whole_grid_buffer_slabs_in_place(A, oracle):
     assert np.array_equal(np.concatenate(idx_all), ridx) and np.array_equal(np.concatenate(rgbn_all), rrgbn)
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("case", ["box24", "human28", "box100", "synth70", "origin_solid"])
+def test_fast_carve_matches_oracle_bfs(A, oracle, golden, case):
+    """fastCarve() (VoxelCarving.cpp:74-167): device flood fill == the oracle's literal BFS, occupied and seen"""
+    from ar_voxel_project_b200.synth import Workload
+    if case in ("box24", "human28", "box100"):
+        ds = "human" if case.startswith("human") else "box"
+        v = golden(f"{ds}_views.npz")
+        P, W, H, bits = v["P"], int(v["W"]), int(v["H"]), v["mask_bits"]
+        if case == "box100":
+            X, Y, Z, s = 100, 100, 50, np.float32(0.0028)
+        else:
+            L = golden(f"{ds}_literal.npz")
+            X, Y, Z, s = int(L["X"]), int(L["Y"]), int(L["Z"]), L["s"]
+    else:
+        X, Y, Z = (70, 33, 41)
+        w = Workload(64, 9, 320, 240, seed=3, dims=(X, Y, Z))
+        P, W, H, bits, s = w.P, w.W, w.H, w.mask_bits.copy(), w.s
+        if case == "origin_solid":
+            bits[:] = 0  # nothing is background: the origin is not carved, the BFS stops at once
+    ro, rs = oracle.fast_carve(X, Y, Z, s, P, W, H, mask_bits=bits)
+    with A.VoxelEngine(X, Y, Z, s) as e:
+        e.set_views(P, W, H)
+        e.set_masks_bits(bits)
+        e.fast_carve()
+        occ, seen = e.download_occupied(), e.download_seen()
+        assert e.stats()["flood_rounds"] >= 1
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+    if case == "origin_solid":
+        assert oracle.unpack(occ, X).all() and oracle.unpack(seen, X).sum() == 1
+    with A.VoxelEngine(X, Y, 2 * Z, s, z_begin=0, z_end=Z) as e:
+        with pytest.raises(A.VoxCarveError):
+            e.fast_carve()  # a slab cannot flood from the origin
