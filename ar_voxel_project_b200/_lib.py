@@ -44,6 +44,8 @@ SIGNATURES = {
     "vc_fast_carve": (C.c_int, [_P, C.c_int32]),
     "vc_color": (C.c_int, [_P, C.c_int32]),
     "vc_mc_classify": (C.c_int, [_P]),
+    "vc_plan_slabs": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "vc_set_slab": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "vc_bind_volumes": (C.c_int, [_P, _P, _P]),
     "vc_device_volumes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "vc_set_gathered": (C.c_int, [_P, C.c_int32]),

@@ -224,8 +224,6 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
     VC_CREATE_CUDA(cudaEventCreate(&e->ev1));
     VC_CREATE_CUDA(cudaEventCreate(&e->evm));
-    VC_CREATE_CUDA(cudaMalloc(&e->d_occ_own, e->slab_words * 4));
-    VC_CREATE_CUDA(cudaMalloc(&e->d_seen_own, e->slab_words * 4));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 8 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
 #undef VC_CREATE_CUDA
@@ -356,8 +354,19 @@ int vc_set_images(vc_engine* e, const uint8_t* images_bgr) {
     return VC_OK;
 }
 
+// engine-owned volumes are allocated on first use (a planning engine, vc_plan_slabs, never needs them)
+static int ensure_volumes(vc_engine* e) {
+    if (e->d_occ_full || e->d_occ_own) return VC_OK;
+    if (bind_device(e)) return VC_ERR_CUDA;
+    VC_CUDA(e, cudaMalloc(&e->d_occ_own, e->slab_words * 4));
+    VC_CUDA(e, cudaMalloc(&e->d_seen_own, e->slab_words * 4));
+    return VC_OK;
+}
+
 // write the Model-constructor state now if a vc_reset is still pending (every reader / writer of the volumes calls this)
 static int materialize_reset(vc_engine* e) {
+    int rcv = ensure_volumes(e);
+    if (rcv) return rcv;
     if (!e->reset_pending) return VC_OK;
     if (bind_device(e)) return VC_ERR_CUDA;
     const long long n = e->slab_words;
@@ -384,7 +393,9 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     if (view_begin < 0 || view_begin > view_end || view_end > e->V)
         return fail(e, VC_ERR_ARG, "vc_carve: bad view range [%d,%d) for V=%d", view_begin, view_end, e->V);
     if (bind_device(e)) return VC_ERR_CUDA;
-    int rc = ensure_constants(e);
+    int rc = ensure_volumes(e);
+    if (rc) return rc;
+    rc = ensure_constants(e);
     if (rc) return rc;
     const int K = 4;
     VcCarveParams p{};
@@ -512,6 +523,79 @@ int vc_fast_carve(vc_engine* e, int32_t mode) {
     return VC_OK;
 }
 
+int vc_set_slab(vc_engine* e, int32_t z_begin, int32_t z_end) {
+    if (!e) return VC_ERR_ARG;
+    if (z_begin < 0 || z_end > e->g.Z || z_begin >= z_end) return fail(e, VC_ERR_ARG, "vc_set_slab: bad z-slab [%d,%d) for Z=%d", z_begin, z_end, e->g.Z);
+    if (bind_device(e)) return VC_ERR_CUDA;
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->g.z_begin = z_begin; e->g.z_end = z_end;
+    e->nz = z_end - z_begin;
+    e->slab_words = e->plane_words * e->nz;
+    // everything sized by the slab is dropped and re-created on demand; views, masks and SAT stay
+    cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); e->d_occ_own = e->d_seen_own = nullptr;
+    cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
+    e->d_bricks = nullptr; e->d_super = nullptr; e->d_brick_flags = nullptr; e->d_super_flags = nullptr; e->d_super_list = nullptr;
+    cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
+    e->d_surf = e->d_counts = e->d_list = nullptr; e->d_block_sums = nullptr;
+    free_color(e);
+    return vc_reset(e);
+}
+
+int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
+    if (!e || !z_bounds) return VC_ERR_ARG;
+    if (n_parts < 1 || n_parts > e->nz) return fail(e, VC_ERR_ARG, "vc_plan_slabs: n_parts=%d outside [1,%d]", n_parts, e->nz);
+    if (e->V == 0 || !e->d_mask) return fail(e, VC_ERR_STATE, "vc_plan_slabs: views and masks must be set first");
+    if (bind_device(e)) return VC_ERR_CUDA;
+    int rc = ensure_constants(e);
+    if (rc) return rc;
+    const int LZ = VC_BZ * VC_SUPER;  // planes per super-brick layer
+    const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+    const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
+    const long long n_super = (long long)sbx * sby * sbz;
+    for (int k = 0; k <= n_parts; k++) z_bounds[k] = e->g.z_begin + (int)((long long)k * e->nz / n_parts);  // uniform fallback
+    if (sbz < n_parts) return VC_OK;  // fewer layers than parts: keep the uniform split
+    VcBrickState* d_states = nullptr;
+    uint8_t* d_flags = nullptr;
+    unsigned int* d_list = nullptr;
+    VC_CUDA(e, cudaMalloc(&d_states, (size_t)n_super * sizeof(VcBrickState)));
+    VC_CUDA(e, cudaMalloc(&d_flags, (size_t)n_super));
+    VC_CUDA(e, cudaMalloc(&d_list, ((size_t)n_super + 1) * sizeof(unsigned int)));
+    VC_CUDA(e, cudaMemsetAsync(d_list + n_super, 0, sizeof(unsigned int), e->stream));
+    VcBrickParams sp{};
+    sp.dense = d_states; sp.super_flags = d_flags; sp.super_list = d_list; sp.n_super_list = d_list + n_super; sp.sat = e->d_sat;
+    sp.X = e->g.X; sp.Y = e->g.Y; sp.Wx = e->Wx; sp.nz = e->nz; sp.z_begin = e->g.z_begin;
+    sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz; sp.W = e->W; sp.H = e->H; sp.v0 = 0; sp.v1 = e->V; sp.s = e->g.voxel_size;
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
+    std::vector<VcBrickState> h((size_t)n_super);
+    cudaError_t s = cudaMemcpyAsync(h.data(), d_states, (size_t)n_super * sizeof(VcBrickState), cudaMemcpyDeviceToHost, e->stream);
+    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
+    cudaFree(d_states); cudaFree(d_flags); cudaFree(d_list);
+    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_plan_slabs: %s", cudaGetErrorString(s));
+    // cost of a layer: undecided views of its undecided super-bricks (per-voxel + brick-level work) plus a small
+    // constant per super-brick (fill pass)
+    std::vector<double> cost((size_t)sbz, 0.0);
+    double total = 0.0;
+    for (int z = 0; z < sbz; z++) {
+        double c = 0.0;
+        for (long long i = 0; i < (long long)sbx * sby; i++) {
+            const VcBrickState& st = h[(size_t)z * sbx * sby + i];
+            c += 0.05;
+            if (!(st.flags & VC_BRICK_CARVED)) c += (double)st.n_und;
+        }
+        cost[z] = c;
+        total += c;
+    }
+    int layer = 0;
+    double acc = 0.0;
+    for (int k = 1; k < n_parts; k++) {
+        const double target = total * k / n_parts;
+        while (layer < sbz - (n_parts - k) && acc + cost[layer] * 0.5 < target) acc += cost[layer++];
+        if (layer < k) { acc += cost[layer]; layer = k; }  // every part gets at least one layer
+        z_bounds[k] = e->g.z_begin + layer * LZ;
+    }
+    return VC_OK;
+}
+
 int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full) {
     if (!e) return VC_ERR_ARG;
     if (!d_occupied_full != !d_seen_full) return fail(e, VC_ERR_ARG, "vc_bind_volumes: bind both volumes or neither");
@@ -550,6 +634,7 @@ int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* se
     if (!occupied || !seen) return fail(e, VC_ERR_ARG, "vc_upload_volumes: null buffer");
     if (n_words != (uint64_t)e->slab_words) return fail(e, VC_ERR_ARG, "vc_upload_volumes: got %llu words, slab has %lld", (unsigned long long)n_words, e->slab_words);
     if (bind_device(e)) return VC_ERR_CUDA;
+    if (ensure_volumes(e)) return VC_ERR_CUDA;
     e->reset_pending = false;  // overwritten entirely
     VC_CUDA(e, cudaMemcpyAsync(e->occ_slab(), occupied, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyAsync(e->seen_slab(), seen, n_words * 4, cudaMemcpyHostToDevice, e->stream));

@@ -16,19 +16,22 @@ def slab_range(rank, world, Z):
     return (rank * Z) // world, ((rank + 1) * Z) // world
 
 
-def all_gather_slabs(full, Z, world=None, group=None):
-    """full: tensor of shape (Z, ...) whose own slab is already filled in. Fills the other slabs in place."""
+def all_gather_slabs(full, Z, world=None, group=None, bounds=None):
+    """full: tensor of shape (Z, ...) whose own slab is already filled in. Fills the other slabs in place.
+    bounds: optional world+1 slab boundaries (e.g. from VoxelEngine.plan_slabs); default = slab_range."""
     world = dist.get_world_size(group) if world is None else world
     if world == 1:
         return full
     rank = dist.get_rank(group)
     flat = full.view(Z, -1)
-    if Z % world == 0:
-        z0, z1 = slab_range(rank, world, Z)
-        dist.all_gather_into_tensor(flat.view(-1), flat[z0:z1].reshape(-1), group=group)
+    if bounds is None:
+        bounds = [slab_range(r, world, Z)[0] for r in range(world)] + [Z]
+    sizes = {bounds[r + 1] - bounds[r] for r in range(world)}
+    if len(sizes) == 1:
+        dist.all_gather_into_tensor(flat.view(-1), flat[bounds[rank]:bounds[rank + 1]].reshape(-1), group=group)
     else:  # ragged slabs: one broadcast per owner
         for r in range(world):
-            a, b = slab_range(r, world, Z)
+            a, b = bounds[r], bounds[r + 1]
             if b > a:
                 dist.broadcast(flat[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
     return full

@@ -152,6 +152,16 @@ class VoxelEngine:
         self._check(self._lib.vc_mc_classify(self._h))
 
     # -- multi-GPU plumbing --------------------------------------------------------------
+    def plan_slabs(self, n_parts):
+        """balanced contiguous z-slab boundaries (n_parts + 1 ints) from the super-brick classification of this engine's range"""
+        b = (C.c_int32 * (n_parts + 1))()
+        self._check(self._lib.vc_plan_slabs(self._h, int(n_parts), b))
+        return list(b)
+
+    def set_slab(self, z_begin, z_end):
+        self._check(self._lib.vc_set_slab(self._h, int(z_begin), int(z_end)))
+        self.z_begin, self.z_end = int(z_begin), int(z_end)
+
     def bind_volumes(self, d_occ_full_ptr, d_seen_full_ptr):
         self._check(self._lib.vc_bind_volumes(self._h, C.c_void_p(d_occ_full_ptr), C.c_void_p(d_seen_full_ptr)))
 

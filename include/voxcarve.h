@@ -122,6 +122,14 @@ VC_EXPORT int vc_color(vc_engine* e, int32_t color_mode);
 VC_EXPORT int vc_mc_classify(vc_engine* e);
 
 /* ---- multi-GPU plumbing ---------------------------------------------------------- */
+/* Balanced contiguous z-slabs for n_parts GPUs.  Runs only the super-brick classification of VC_EXACT over this engine's
+ * z-range (needs views + masks, allocates no volumes), estimates the work per layer of 32 planes and returns n_parts+1
+ * boundaries (interior ones multiples of 32 planes from z_begin) with z_bounds[0] = z_begin, z_bounds[n_parts] = z_end.
+ * Deterministic: every rank computes the same split from the same inputs. */
+VC_EXPORT int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds);
+/* Re-range an engine to the slab [z_begin, z_end) of the same grid, keeping views, masks and SAT (plan on the whole grid,
+ * then narrow). The volumes are reset. */
+VC_EXPORT int vc_set_slab(vc_engine* e, int32_t z_begin, int32_t z_end);
 /* Use caller-owned device buffers holding the WHOLE grid (Z*Y*Wx words each); the engine
  * carves its slab in place at word offset z_begin*Y*Wx, so an all-gather of the slabs is in
  * place, and colour / MC passes read neighbour planes from the gathered buffer. */

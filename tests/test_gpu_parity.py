@@ -360,3 +360,31 @@ def test_fast_carve_matches_oracle_bfs(A, oracle, golden, case):
     with A.VoxelEngine(X, Y, 2 * Z, s, z_begin=0, z_end=Z) as e:
         with pytest.raises(A.VoxCarveError):
             e.fast_carve()  # a slab cannot flood from the origin
+
+
+def test_planned_slabs_tile_the_grid_and_match(A, oracle):
+    """vc_plan_slabs / vc_set_slab: balanced contiguous slabs (boundaries on 32-plane layers) carve to the same bits"""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 96, 64, 160
+    w = Workload(160, 8, 320, 240, seed=6, dims=(X, Y, Z))
+    with A.VoxelEngine(X, Y, Z, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        e.carve()
+        full = e.download_occupied(), e.download_seen()
+        for n in (1, 2, 3, 5):
+            b = e.plan_slabs(n)
+            assert b[0] == 0 and b[-1] == Z and all(x < y for x, y in zip(b[:-1], b[1:])) and all(x % 32 == 0 for x in b[:-1])
+        with pytest.raises(A.VoxCarveError):
+            e.plan_slabs(Z + 1)
+        b = e.plan_slabs(3)
+        parts = []
+        for z0, z1 in zip(b[:-1], b[1:]):
+            e.set_slab(z0, z1)
+            e.carve()
+            parts.append((e.download_occupied(), e.download_seen()))
+            assert parts[-1][0].shape[0] == z1 - z0
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=64, z1=70)
+    assert np.array_equal(full[0][64:70], ro) and np.array_equal(full[1][64:70], rs)
