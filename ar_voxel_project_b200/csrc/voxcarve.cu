@@ -67,6 +67,12 @@ struct vc_engine {
     bool have_colors = false;
     unsigned long long* d_hist = nullptr;
     bool have_mc = false;
+    // dense RGBA model ("next" rows)
+    float4 *d_dense = nullptr, *d_dense_tmp = nullptr;
+    float* d_mesh_verts = nullptr;
+    uint32_t* d_mesh_rgb = nullptr;
+    unsigned long long n_mesh_tris = 0;
+    bool have_dense = false, have_mesh = false;
     vc_stats stats{};
     std::string err;
 
@@ -241,6 +247,7 @@ void vc_destroy(vc_engine* e) {
     cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist);
+    cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -843,6 +850,143 @@ int vc_measure_peaks(int32_t device, double* ffma_tflops, double* dfma_tflops) {
     if (s != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_measure_peaks: %s", cudaGetErrorString(s));
     *ffma_tflops = best[0];
     *dfma_tflops = best[1];
+    return VC_OK;
+}
+
+static int dense_ready(vc_engine* e, const char* who, bool need_data) {
+    if (!e->whole_grid()) return fail(e, VC_ERR_STATE, "%s: the dense Model needs the whole grid on one engine", who);
+    if (bind_device(e)) return VC_ERR_CUDA;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    if (!e->d_dense) VC_CUDA(e, cudaMalloc(&e->d_dense, n * sizeof(float4)));
+    if (need_data && !e->have_dense) return fail(e, VC_ERR_STATE, "%s: no dense Model yet (vc_dense_upload / vc_dense_from_volumes)", who);
+    static std::mutex m;
+    static bool tables[64] = {};
+    std::lock_guard<std::mutex> lk(m);
+    if (!tables[e->g.device & 63]) {  // triTable -> constant memory, once per device
+        signed char tri[256][16];
+        unsigned char ntri[256];
+        for (int i = 0; i < 256; i++) {
+            int k = 0;
+            for (; k < 16; k++) {
+                const char c = VC_TRI_TABLE_HEX[i * 16 + k];
+                tri[i][k] = c == 'f' ? -1 : (signed char)(c <= '9' ? c - '0' : c - 'a' + 10);
+            }
+            int nt = 0;
+            while (nt < 16 && tri[i][nt] != -1) nt++;
+            ntri[i] = (unsigned char)(nt / 3);
+        }
+        VC_CUDA(e, cudaMemcpyToSymbol(c_tri, tri, sizeof tri));
+        VC_CUDA(e, cudaMemcpyToSymbol(c_ntri, ntri, sizeof ntri));
+        tables[e->g.device & 63] = true;
+    }
+    return VC_OK;
+}
+
+int vc_dense_upload(vc_engine* e, const float* rgba) {
+    if (!e) return VC_ERR_ARG;
+    if (!rgba) return fail(e, VC_ERR_ARG, "vc_dense_upload: null buffer");
+    int rc = dense_ready(e, "vc_dense_upload", false);
+    if (rc) return rc;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    VC_CUDA(e, cudaMemcpyAsync(e->d_dense, rgba, n * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->have_dense = true; e->have_mesh = false;
+    return VC_OK;
+}
+
+int vc_dense_from_volumes(vc_engine* e, int32_t apply_colors, int32_t handle_unseen) {
+    if (!e) return VC_ERR_ARG;
+    int rc = dense_ready(e, "vc_dense_from_volumes", false);
+    if (rc) return rc;
+    if (apply_colors && !e->have_colors) return fail(e, VC_ERR_STATE, "vc_dense_from_volumes: apply_colors needs a preceding vc_color");
+    rc = materialize_reset(e);
+    if (rc) return rc;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    VcDense d{e->d_dense, e->g.X, e->g.Y, e->g.Z};
+    vc_dense_base_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, e->occ_slab(), e->Wx);
+    if (apply_colors && e->n_surface)
+        vc_dense_colors_kernel<<<(unsigned)((e->n_surface + 255) / 256), 256, 0, e->stream>>>(d, e->d_color_idx, e->d_color_rgbn, e->n_surface);
+    if (handle_unseen) vc_dense_unseen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, e->seen_slab(), e->Wx);
+    VC_CUDA(e, cudaGetLastError());
+    e->have_dense = true; e->have_mesh = false;
+    return VC_OK;
+}
+
+int vc_dense_closure(vc_engine* e, int32_t kernel_size) {
+    if (!e) return VC_ERR_ARG;
+    if (kernel_size < 1 || kernel_size % 2 != 1) return fail(e, VC_ERR_ARG, "Invalid kernel size for post processing, skipping...");  // Postprocessing3d.cpp:8-11
+    int rc = dense_ready(e, "vc_dense_closure", true);
+    if (rc) return rc;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    if (!e->d_dense_tmp) VC_CUDA(e, cudaMalloc(&e->d_dense_tmp, n * sizeof(float4)));
+    VcDense d{e->d_dense, e->g.X, e->g.Y, e->g.Z};
+    vc_closure_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, e->d_dense_tmp, (kernel_size - 1) / 2);
+    VC_CUDA(e, cudaGetLastError());
+    std::swap(e->d_dense, e->d_dense_tmp);
+    e->have_mesh = false;
+    return VC_OK;
+}
+
+int vc_dense_download(vc_engine* e, float* rgba) {
+    if (!e) return VC_ERR_ARG;
+    if (!rgba) return fail(e, VC_ERR_ARG, "vc_dense_download: null buffer");
+    int rc = dense_ready(e, "vc_dense_download", true);
+    if (rc) return rc;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    VC_CUDA(e, cudaMemcpyAsync(rgba, e->d_dense, n * sizeof(float4), cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return VC_OK;
+}
+
+int vc_mc_mesh(vc_engine* e, float threshold, uint64_t* n_triangles) {
+    if (!e || !n_triangles) return VC_ERR_ARG;
+    int rc = dense_ready(e, "vc_mc_mesh", true);
+    if (rc) return rc;
+    const long long ncol = (long long)(e->g.X + 1) * (e->g.Y + 1);
+    if (ncol > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "vc_mc_mesh: grid too large");
+    const int nb = (int)((ncol + VC_SCAN_BLOCK - 1) / VC_SCAN_BLOCK);
+    uint32_t* d_counts = nullptr;
+    unsigned long long* d_sums = nullptr;
+    VC_CUDA(e, cudaMalloc(&d_counts, (size_t)ncol * 4));
+    VC_CUDA(e, cudaMalloc(&d_sums, ((size_t)nb + 1) * sizeof(unsigned long long)));
+    VcDense d{e->d_dense, e->g.X, e->g.Y, e->g.Z};
+    vc_mc_count_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, e->stream>>>(d, threshold, d_counts);
+    vc_scan_block_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(d_counts, d_counts, d_sums, ncol);
+    vc_scan_sums_kernel<<<1, 1024, 0, e->stream>>>(d_sums, nb, d_sums + nb);
+    vc_scan_add_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(d_counts, d_sums, ncol);
+    unsigned long long total = 0;
+    cudaError_t s = cudaMemcpyAsync(&total, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, e->stream);
+    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
+    if (s == cudaSuccess && total > 0xffffffffull) { cudaFree(d_counts); cudaFree(d_sums); return fail(e, VC_ERR_CAPACITY, "vc_mc_mesh: %llu triangles exceed 32-bit offsets", total); }
+    if (s == cudaSuccess) {
+        cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb); e->d_mesh_verts = nullptr; e->d_mesh_rgb = nullptr;
+        if (total) {
+            s = cudaMalloc(&e->d_mesh_verts, total * 9 * sizeof(float));
+            if (s == cudaSuccess) s = cudaMalloc(&e->d_mesh_rgb, total * 3 * sizeof(uint32_t));
+            if (s == cudaSuccess) {
+                vc_mc_emit_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, e->stream>>>(d, threshold, d_counts, e->d_mesh_verts, e->d_mesh_rgb);
+                s = cudaStreamSynchronize(e->stream);
+            }
+        }
+    }
+    cudaFree(d_counts); cudaFree(d_sums);
+    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_mc_mesh: %s", cudaGetErrorString(s));
+    e->n_mesh_tris = total;
+    e->have_mesh = true;
+    *n_triangles = total;
+    return VC_OK;
+}
+
+int vc_download_mesh(vc_engine* e, float* verts, uint32_t* rgb, uint64_t capacity_triangles) {
+    if (!e) return VC_ERR_ARG;
+    if (!e->have_mesh) return fail(e, VC_ERR_STATE, "vc_download_mesh: run vc_mc_mesh first");
+    if (capacity_triangles < e->n_mesh_tris) return fail(e, VC_ERR_CAPACITY, "vc_download_mesh: capacity %llu < %llu triangles", (unsigned long long)capacity_triangles, e->n_mesh_tris);
+    if (e->n_mesh_tris == 0) return VC_OK;
+    if (!verts || !rgb) return fail(e, VC_ERR_ARG, "vc_download_mesh: null buffer");
+    if (bind_device(e)) return VC_ERR_CUDA;
+    VC_CUDA(e, cudaMemcpyAsync(verts, e->d_mesh_verts, e->n_mesh_tris * 9 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaMemcpyAsync(rgb, e->d_mesh_rgb, e->n_mesh_tris * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
     return VC_OK;
 }
 

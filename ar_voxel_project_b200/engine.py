@@ -215,6 +215,32 @@ class VoxelEngine:
         self._check(self._lib.vc_download_mc(self._h, C.c_void_p(hist.ctypes.data), C.byref(na), C.byref(nt)))
         return hist, na.value, nt.value
 
+    # -- "next" rows: dense Model, closure, marching-cubes mesh ------------------------
+    def dense_upload(self, rgba):
+        n = self.X * self.Y * self.Z * 16
+        a, keep = _host_ptr(np.ascontiguousarray(rgba, np.float32), np.float32, n, "dense rgba")
+        self._check(self._lib.vc_dense_upload(self._h, C.c_void_p(a)))
+
+    def dense_from_volumes(self, apply_colors=False, handle_unseen=False):
+        self._check(self._lib.vc_dense_from_volumes(self._h, int(bool(apply_colors)), int(bool(handle_unseen))))
+
+    def dense_closure(self, kernel_size=3):
+        self._check(self._lib.vc_dense_closure(self._h, int(kernel_size)))
+
+    def dense_download(self):
+        out = np.empty((self.X * self.Y * self.Z, 4), np.float32)
+        self._check(self._lib.vc_dense_download(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def mc_mesh(self, threshold=0.5):
+        """-> (verts float32[T,3,3] in voxel-index coordinates, rgb uint32[T,3]) in the reference's emission order"""
+        n = C.c_uint64()
+        self._check(self._lib.vc_mc_mesh(self._h, C.c_float(threshold), C.byref(n)))
+        verts = np.empty((n.value, 3, 3), np.float32)
+        rgb = np.empty((n.value, 3), np.uint32)
+        self._check(self._lib.vc_download_mesh(self._h, C.c_void_p(verts.ctypes.data), C.c_void_p(rgb.ctypes.data), n.value))
+        return verts, rgb
+
     def stats(self):
         s = L.Stats()
         self._check(self._lib.vc_get_stats(self._h, C.byref(s)))

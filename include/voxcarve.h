@@ -158,6 +158,21 @@ VC_EXPORT int vc_download_colors(vc_engine* e, uint64_t* idx, uint8_t* rgbn, uin
 VC_EXPORT int vc_download_mc(vc_engine* e, uint64_t hist256[256], uint64_t* n_active, uint64_t* n_triangles);
 VC_EXPORT int vc_get_stats(vc_engine* e, vc_stats* out);
 
+/* ---- "next" rows: dense RGBA Model on the device, applyClosure, marchingCubes triangles (whole grid only) ---- */
+/* Load the reference Model's voxels (its RGBA float vector, X*Y*Z*4 floats, index = Model::flatten, Model.h:100-106). */
+VC_EXPORT int vc_dense_upload(vc_engine* e, const float* rgba);
+/* Build the Model's voxels from the device volumes: occupied -> MODEL_COLOR, carved -> 0 (Model.h:90, VoxelCarving.cpp:52);
+ * apply_colors != 0: the records of the last vc_color (ColorReconstruction.cpp:41,66); handle_unseen != 0:
+ * Model::handleUnseen (Model.cpp:36-47). */
+VC_EXPORT int vc_dense_from_volumes(vc_engine* e, int32_t apply_colors, int32_t handle_unseen);
+/* applyClosure(model, kernelSize) (Postprocessing3d.h:10): returns VC_ERR_ARG for an even kernel size (reference: -1). */
+VC_EXPORT int vc_dense_closure(vc_engine* e, int32_t kernel_size);
+VC_EXPORT int vc_dense_download(vc_engine* e, float* rgba);
+/* marchingCubes(model, ..., threshold) geometry (MarchingCubes.h:596, MarchingCubes.cpp:8-19): triangles in the reference's
+ * emission order, 3 unshared vertices each (voxel-index coordinates, before WriteMesh's scale/translation) + face colour. */
+VC_EXPORT int vc_mc_mesh(vc_engine* e, float threshold, uint64_t* n_triangles);
+VC_EXPORT int vc_download_mesh(vc_engine* e, float* verts /* T*9 */, uint32_t* rgb /* T*3 */, uint64_t capacity_triangles);
+
 /* ---- measurement helper (bench.py roofline denominators) ------------------------- */
 /* Register-resident FFMA and DFMA loops on `device`: measured CUDA-core peaks in TFLOP/s
  * (2 flops per FMA), timed with CUDA events, best of 5. Not part of the carve path. */

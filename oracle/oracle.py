@@ -43,6 +43,10 @@ def lib():
         L.vo_mc_classify.argtypes = [C.c_int] * 3 + [u32p, u8p, u64p, u64p, u64p]
         L.vo_pixel_of.argtypes = [f32p] + [C.c_int] * 3 + [C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), f32p]
         L.vo_max_threads.restype = C.c_int
+        L.vo_closure.argtypes = [C.c_int] * 4 + [f32p, f32p]
+        L.vo_marching_cubes.argtypes = [C.c_int] * 3 + [f32p, C.c_float, np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS"), f32p, u32p, C.c_uint64]
+        L.vo_marching_cubes.restype = C.c_uint64
+        L.vo_write_off.argtypes = [C.c_char_p, C.c_uint64, f32p, u32p] + [C.c_float] * 4
         _lib = L
     return _lib
 
@@ -143,3 +147,53 @@ def unpack(words, X):
     """uint32[..., Wx] -> bool[..., X]"""
     b = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little").reshape(*words.shape[:-1], -1)
     return b[..., :X].astype(bool)
+
+
+def tri_table():
+    """triTable as int8[256,16] (-1 terminated), parsed from the packed table the product also ships"""
+    txt = open(os.path.join(_HERE, "..", "ar_voxel_project_b200", "csrc", "mc_tables.inc")).read()
+    hexs = "".join(part for part in txt.split('"')[1::2])
+    return np.array([[-1 if c == "f" else int(c, 16) for c in hexs[i * 16:(i + 1) * 16]] for i in range(256)], np.int8)
+
+
+def closure(X, Y, Z, rgba, kernel_size=3):
+    """applyClosure on a dense RGBA model float32[X*Y*Z, 4] (flatten order). -> new array"""
+    a = np.ascontiguousarray(rgba, np.float32).reshape(-1)
+    out = np.empty_like(a)
+    rc = lib().vo_closure(X, Y, Z, kernel_size, a, out)
+    if rc != 0:
+        raise ValueError("Invalid kernel size for post processing")
+    return out.reshape(-1, 4)
+
+
+def marching_cubes(X, Y, Z, rgba, threshold=0.5):
+    """-> (verts float32[T,3,3], rgb uint32[T,3])"""
+    a = np.ascontiguousarray(rgba, np.float32).reshape(-1)
+    tt = np.ascontiguousarray(tri_table())
+    n = lib().vo_marching_cubes(X, Y, Z, a, threshold, tt, np.empty(9, np.float32), np.empty(3, np.uint32), 0)
+    verts = np.empty(max(n, 1) * 9, np.float32)
+    rgb = np.empty(max(n, 1) * 3, np.uint32)
+    n2 = lib().vo_marching_cubes(X, Y, Z, a, threshold, tt, verts, rgb, n)
+    assert n2 == n
+    return verts[:n * 9].reshape(n, 3, 3), rgb[:n * 3].reshape(n, 3)
+
+
+def write_off(path, verts, rgb, scale=1.0, translation=(0.0, 0.0, 0.0)):
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1)
+    c = np.ascontiguousarray(rgb, np.uint32).reshape(-1)
+    rc = lib().vo_write_off(path.encode(), len(c) // 3, v, c, float(np.float32(scale)), *[float(np.float32(t)) for t in translation])
+    if rc != 0:
+        raise OSError(f"cannot write {path}")
+
+
+def dense_model(X, Y, Z, occ_words, seen_words=None, color_idx=None, color_rgbn=None):
+    """the reference Model's voxels after carve [+ colour pass] [+ handleUnseen] (Model.cpp:9-14,36-47): float32[X*Y*Z,4]"""
+    occ = unpack(occ_words, X).reshape(-1)
+    rgba = np.tile(np.array([50, 168, 141, 1], np.float32), (X * Y * Z, 1))
+    rgba[~occ] = 0
+    if color_idx is not None:
+        m = color_rgbn[:, 3] > 0
+        rgba[color_idx[m].astype(np.int64), :3] = color_rgbn[m, :3]
+    if seen_words is not None:
+        rgba[~unpack(seen_words, X).reshape(-1)] = (204, 0, 0, 1)
+    return rgba

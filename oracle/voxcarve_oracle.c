@@ -18,6 +18,7 @@
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off -pthread)
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -318,4 +319,121 @@ VO_API void vo_mc_classify(int X, int Y, int Z, const uint32_t* occ, const uint8
                 if (idx != 0 && idx != 255) (*n_active)++; /* edgeTable[idx] != 0 (:486) */
                 *n_tris += tri_count256[idx];
             }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" rows of the hot path: applyClosure and the full marchingCubes on the dense
+ * RGBA Model (std::vector<Vector4f> voxels, index = Model::flatten = x + X*(y + Y*z), Model.h:104-106).
+ * ---------------------------------------------------------------------------------------------- */
+static inline const float* vget(const float* rgba, int X, int Y, int Z, int x, int y, int z) {
+    static const float zero[4] = {0, 0, 0, 0}; /* Model::get out of range (Model.h:119-122) */
+    if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z) return zero;
+    return rgba + 4 * ((size_t)x + (size_t)X * ((size_t)y + (size_t)Y * (size_t)z));
+}
+
+/* applyClosure(model, kernelSize) Postprocessing3d.cpp:4-100.  "Dilution" (:20-58): a voxel with w > 0 is kept,
+ * any other becomes the mean (sum / count, f32, neighbours visited x, y, z = outer..inner) of its in-grid
+ * neighbours with w > 0, or (0,0,0,0).  The erosion (:60-96) tests `w < thresh` with thresh = 0 and can never
+ * fire, so the model becomes the dilated copy.  Returns -1 for an even kernel size (:8-11). */
+VO_API int vo_closure(int X, int Y, int Z, int kernelSize, const float* in, float* out) {
+    if (kernelSize % 2 != 1) return -1;
+    const int size = (kernelSize - 1) / 2;
+    for (int x = 0; x < X; x++)
+        for (int y = 0; y < Y; y++)
+            for (int z = 0; z < Z; z++) {
+                const float* o = vget(in, X, Y, Z, x, y, z);
+                float* dst = out + 4 * ((size_t)x + (size_t)X * ((size_t)y + (size_t)Y * (size_t)z));
+                if (o[3] > 0.0f) { memcpy(dst, o, 16); continue; }
+                int count = 0;
+                float sum[4] = {0, 0, 0, 0};
+                for (int i = -size; i <= size; i++) {
+                    int xn = x + i;
+                    if (xn < 0 || xn >= X) continue;
+                    for (int j = -size; j <= size; j++) {
+                        int yn = y + j;
+                        if (yn < 0 || yn >= Y) continue;
+                        for (int k = -size; k <= size; k++) {
+                            int zn = z + k;
+                            if (zn < 0 || zn >= Z) continue;
+                            const float* v = vget(in, X, Y, Z, xn, yn, zn);
+                            if (v[3] > 0.0f) { count++; for (int c = 0; c < 4; c++) sum[c] = sum[c] + v[c]; }
+                        }
+                    }
+                }
+                if (count > 0) for (int c = 0; c < 4; c++) sum[c] = sum[c] / (float)count;
+                memcpy(dst, sum, 16);
+            }
+    return 0;
+}
+
+static int is_default_color(const float* c) { /* MODEL_COLOR / UNSEEN_COLOR heads (Model.h:90-91, MarchingCubes.h:453,457) */
+    return (c[0] == 50.0f && c[1] == 168.0f && c[2] == 141.0f) || (c[0] == 204.0f && c[1] == 0.0f && c[2] == 0.0f);
+}
+
+/* VertexInterp MarchingCubes.h:428-468 */
+static void vertex_interp(float thr, const float* p0, const float* v0, const float* p1, const float* v1, float* coord, float* color) {
+    if (v0[3] == 0.0f && v1[3] != 0.0f) { memcpy(color, v1, 12); memcpy(coord, p1, 12); return; }
+    if (v0[3] != 0.0f && v1[3] == 0.0f) { memcpy(color, v0, 12); memcpy(coord, p0, 12); return; }
+    float f = (v0[3] == v1[3]) ? 0.5f : (thr - v0[3]) / (v1[3] - v0[3]);
+    for (int c = 0; c < 3; c++) coord[c] = (1 - f) * p0[c] + f * p1[c];
+    if (is_default_color(v0)) memcpy(color, v1, 12);
+    else if (is_default_color(v1)) memcpy(color, v0, 12);
+    else for (int c = 0; c < 3; c++) color[c] = (1 - f) * v0[c] + f * v1[c];
+}
+
+/* marchingCubes() MarchingCubes.cpp:8-31 -> ProcessVoxel MarchingCubes.h:532-578 -> Polygonise :478-511.
+ * tri_table = triTable (256 x 16, -1 terminated, MarchingCubes.h:147-404); edgeTable follows from the topology.
+ * Output per triangle, in the reference's emission order (x outer, y, z inner): 9 floats (3 unshared vertices, :561-568)
+ * and 3 colours MeanColorFloats (:414-416, :570-573, incl. the col[2] = vertex i+1 quirk :506). Returns #triangles. */
+VO_API uint64_t vo_marching_cubes(int X, int Y, int Z, const float* rgba, float thr, const int8_t* tri_table, float* verts,
+                                  uint32_t* rgb, uint64_t cap) {
+    static const int second[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    uint64_t n = 0;
+    for (int x = -1; x < X; x++)
+        for (int y = -1; y < Y; y++)
+            for (int z = -1; z < Z; z++) {
+                const int cx[8] = {x + 1, x, x, x + 1, x + 1, x, x, x + 1}, cy[8] = {y, y, y + 1, y + 1, y, y, y + 1, y + 1},
+                          cz[8] = {z, z, z, z, z + 1, z + 1, z + 1, z + 1};
+                const float* val[8];
+                float p[8][3];
+                int idx = 0;
+                for (int i = 0; i < 8; i++) {
+                    val[i] = vget(rgba, X, Y, Z, cx[i], cy[i], cz[i]);
+                    p[i][0] = (float)cx[i]; p[i][1] = (float)cy[i]; p[i][2] = (float)cz[i];
+                    if (val[i][3] < thr) idx |= 1 << i;
+                }
+                int edges = 0;
+                for (int e = 0; e < 12; e++) if (((idx >> (e % 8)) & 1) != ((idx >> second[e]) & 1)) edges |= 1 << e;
+                if (edges == 0) continue;
+                float vc[12][3], vcol[12][3];
+                for (int e = 0; e < 12; e++)
+                    if (edges & (1 << e)) vertex_interp(thr, p[e % 8], val[e % 8], p[second[e]], val[second[e]], vc[e], vcol[e]);
+                const int8_t* t = tri_table + idx * 16;
+                for (int i = 0; t[i] != -1; i += 3) {
+                    if (n < cap) {
+                        for (int k = 0; k < 3; k++) memcpy(verts + n * 9 + k * 3, vc[t[i + k]], 12);
+                        const float *c0 = vcol[t[i]], *c1 = vcol[t[i + 1]], *c2 = vcol[t[i + 1]];
+                        for (int c = 0; c < 3; c++) rgb[n * 3 + c] = (uint32_t)roundf(((c0[c] + c1[c]) + c2[c]) / 3);
+                    }
+                    n++;
+                }
+            }
+    return n;
+}
+
+/* SimpleMesh::WriteMesh MarchingCubes.h:59-87: text .off, ostream default float formatting (== printf %g). */
+VO_API int vo_write_off(const char* path, uint64_t ntris, const float* verts, const uint32_t* rgb, float scale, float tx, float ty, float tz) {
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    fprintf(f, "OFF\n%llu %llu 0\n", (unsigned long long)(ntris * 3), (unsigned long long)ntris);
+    for (uint64_t i = 0; i < ntris * 3; i++) {
+        float a = verts[i * 3] * scale, b = verts[i * 3 + 1] * scale, c = verts[i * 3 + 2] * scale;
+        a = a + tx; b = b + ty; c = c + tz;
+        fprintf(f, "%g %g %g\n", a, b, c);
+    }
+    for (uint64_t i = 0; i < ntris; i++)
+        fprintf(f, "3 %llu %llu %llu %u %u %u\n", (unsigned long long)(3 * i), (unsigned long long)(3 * i + 1), (unsigned long long)(3 * i + 2),
+                rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2]);
+    fclose(f);
+    return 0;
 }
