@@ -6,6 +6,7 @@
 //     vc::carve / vc::fastCarve                          VoxelCarving.h:19,31
 //     vc::reconstructClosestColor / reconstructAvgColor   ColorReconstruction.h:131,142
 //     vc::marchingCubesClassify                           cube-index half of MarchingCubes.h:596
+//     vc::applyClosure / vc::marchingCubes                Postprocessing3d.h:10, MarchingCubes.h:596 (incl. the .off writer)
 // ModelT must offer what Model.h offers: getX(), getY(), getZ(), getSize(), get(x,y,z) returning a
 // 4-vector with operator()(int) and a (float,float,float,float) constructor, set(x,y,z,vec), see(x,y,z).
 // The per-dataset inputs the reference recomputes inside every call (estimatePoseFromImage +
@@ -17,6 +18,7 @@
 #define VOXCARVE_HOST_HPP
 
 #include <cstdint>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -91,6 +93,18 @@ class Engine {
         rgbn.resize(n * 4);
         check(vc_download_colors(h_, idx.data(), rgbn.data(), n));
     }
+    // "next" rows: dense RGBA Model on the device
+    void denseUpload(const std::vector<float>& rgba) { check(vc_dense_upload(h_, rgba.data())); }
+    void denseClosure(int kernelSize) { check(vc_dense_closure(h_, kernelSize)); }
+    void denseDownload(std::vector<float>& rgba) { check(vc_dense_download(h_, rgba.data())); }
+    uint64_t mcMesh(float threshold, std::vector<float>& verts, std::vector<uint32_t>& rgb) {
+        uint64_t n = 0;
+        check(vc_mc_mesh(h_, threshold, &n));
+        verts.resize(n * 9);
+        rgb.resize(n * 3);
+        check(vc_download_mesh(h_, verts.data(), rgb.data(), n));
+        return n;
+    }
     vc_stats stats() { vc_stats s{}; check(vc_get_stats(h_, &s)); return s; }
     vc_engine* handle() { return h_; }
     int wordsPerRow() const { return (X_ + 31) / 32; }
@@ -130,6 +144,21 @@ std::vector<uint32_t> packOccupancy(ModelT& model) {
             for (int x = 0; x < X; x++)
                 if (model.get(x, y, z)(3) != 0) occ[((size_t)z * Y + y) * Wx + (x >> 5)] |= 1u << (x & 31);
     return occ;
+}
+
+// the Model's voxels as X*Y*Z*4 floats in Model::flatten order (Model.h:104-106)
+template <class ModelT>
+std::vector<float> packVoxels(ModelT& model) {
+    const int X = model.getX(), Y = model.getY(), Z = model.getZ();
+    std::vector<float> rgba((size_t)X * Y * Z * 4);
+    for (int z = 0; z < Z; z++)
+        for (int y = 0; y < Y; y++)
+            for (int x = 0; x < X; x++) {
+                const auto v = model.get(x, y, z);
+                float* o = &rgba[4 * ((size_t)x + (size_t)X * ((size_t)y + (size_t)Y * z))];
+                o[0] = v(0); o[1] = v(1); o[2] = v(2); o[3] = v(3);
+            }
+    return rgba;
 }
 
 template <class ModelT>
@@ -208,6 +237,60 @@ McSummary marchingCubesClassify(ModelT& model) {
     const McSummary s = e.mcClassify();
     std::cout << "LOG - MC: voxel processing completed." << std::endl;
     return s;
+}
+
+// applyClosure() — Postprocessing3d.h:10, Postprocessing3d.cpp:4-100. Returns -1 for an even kernel size, like the reference.
+template <class ModelT>
+int applyClosure(ModelT* model, int kernelSize) {
+    std::cout << "LOG - PP: starting postprocessing." << std::endl;
+    if (kernelSize % 2 != 1) {
+        std::cerr << "Invalid kernel size for post processing, skipping..." << std::endl;
+        return -1;
+    }
+    const int X = model->getX(), Y = model->getY(), Z = model->getZ();
+    Engine e(X, Y, Z, model->getSize());
+    std::vector<float> rgba = detail::packVoxels(*model);
+    e.denseUpload(rgba);
+    e.denseClosure(kernelSize);
+    e.denseDownload(rgba);
+    for (int z = 0; z < Z; z++)
+        for (int y = 0; y < Y; y++)
+            for (int x = 0; x < X; x++) {
+                const float* o = &rgba[4 * ((size_t)x + (size_t)X * ((size_t)y + (size_t)Y * z))];
+                model->set(x, y, z, detail::Vec4Of<ModelT>(o[0], o[1], o[2], o[3]));
+            }
+    std::cout << "LOG - PP: postprocessing completed." << std::endl;
+    return 0;
+}
+
+// marchingCubes() — MarchingCubes.h:596, MarchingCubes.cpp:8-31 + SimpleMesh::WriteMesh MarchingCubes.h:59-87.
+// translation = {tx, ty, tz}. Returns false if the file cannot be written.
+template <class ModelT>
+bool marchingCubes(ModelT* model, float scale = 1.0f, const float* translation = nullptr, float threshold = 0.5f,
+                   const std::string& outFileName = "out/mesh.off") {
+    std::cout << "LOG - MC: starting to process Voxels." << std::endl;
+    Engine e(model->getX(), model->getY(), model->getZ(), model->getSize());
+    e.denseUpload(detail::packVoxels(*model));
+    std::vector<float> verts;
+    std::vector<uint32_t> rgb;
+    const uint64_t nt = e.mcMesh(threshold, verts, rgb);
+    std::cout << "LOG - MC: voxel processing completed.\n Writing mesh..." << std::endl;
+    const float sf = scale * model->getSize();
+    const float tx = translation ? translation[0] : 0.f, ty = translation ? translation[1] : 0.f, tz = translation ? translation[2] : 0.f;
+    std::ofstream outFile(outFileName);
+    if (!outFile.is_open()) {
+        std::cout << "ERR - MC: unable to write output file!" << std::endl;
+        return false;
+    }
+    outFile << "OFF" << std::endl;
+    outFile << nt * 3 << " " << nt << " 0" << std::endl;
+    for (uint64_t i = 0; i < nt * 3; i++)
+        outFile << verts[i * 3] * sf + tx << " " << verts[i * 3 + 1] * sf + ty << " " << verts[i * 3 + 2] * sf + tz << std::endl;
+    for (uint64_t i = 0; i < nt; i++)
+        outFile << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << " " << rgb[i * 3] << " " << rgb[i * 3 + 1] << " " << rgb[i * 3 + 2] << std::endl;
+    outFile.close();
+    std::cout << "LOG - MC: Mesh written, marchingCubes completed." << std::endl;
+    return true;
 }
 
 }  // namespace vc

@@ -39,7 +39,8 @@ def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
         vs.mask_bits.astype(np.uint32).tofile(f)
         vs.images_bgr.astype(np.uint8).tofile(f)
     out = tmp_path / "out.bin"
-    subprocess.check_call([_build(tmp_path, lib_built), str(case), str(out)])
+    off = tmp_path / "mesh.off"
+    subprocess.check_call([_build(tmp_path, lib_built), str(case), str(out), str(off)], stdout=subprocess.DEVNULL)
     raw = open(out, "rb").read()
     n = X * Y * Z
     vox = np.frombuffer(raw, np.float32, n * 4).reshape(n, 4)
@@ -61,3 +62,11 @@ def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
     rh, _, rnt = oracle.mc_classify(X, Y, Z, ro)
     assert np.array_equal(hist, rh) and ntris == rnt
     assert nv == vs.V and per_view[-1] == rnt  # -intermediateMesh: the last per-view summary is the final one
+    # applyClosure(&model, 3) + marchingCubes(&model, 1.5, (0.5,-0.25,2), 0.5, file): the .off text equals the oracle's
+    dense = exp.copy()
+    full = np.concatenate([dense, (vox[:, 3:4] != 0).astype(np.float32)], axis=1)
+    closed = oracle.closure(X, Y, Z, full, 3)
+    rv, rc = oracle.marching_cubes(X, Y, Z, closed, 0.5)
+    ref = tmp_path / "ref.off"
+    oracle.write_off(str(ref), rv, rc, np.float32(1.5) * s, (0.5, -0.25, 2.0))
+    assert open(off).read() == open(ref).read()

@@ -159,3 +159,36 @@ def test_soft_golden_box_mesh(oracle, golden):
     from ar_voxel_project_b200.synth import pack_bits
     _, _, ntris = oracle.mc_classify(100, 100, 50, pack_bits(closed))
     assert abs(ntris - soft["faces"]) / soft["faces"] < 0.005, ntris
+
+
+def test_full_pipeline_against_soft_golden_mesh(oracle, golden, tmp_path):
+    """carve -> handleUnseen -> applyClosure(3) -> marchingCubes -> WriteMesh on box_dataset at 100x100x50 (the command behind
+    generated_models/1.off). Soft: the golden's poses come from another OpenCV build. File layout, number formatting and the
+    first lines are identical; >= 95 % of the golden's vertex multiset is reproduced; all faces carry MODEL_COLOR."""
+    v, g = golden("box_views.npz"), golden("soft_box_1off_vertices.npz")
+    s = np.float32(0.0028)
+    occ, seen = oracle.carve(100, 100, 50, s, v["P"], int(v["W"]), int(v["H"]), mask_bits=v["mask_bits"], nthreads=0)
+    m = oracle.closure(100, 100, 50, oracle.dense_model(100, 100, 50, occ, seen), 3)
+    verts, rgb = oracle.marching_cubes(100, 100, 50, m, 0.5)
+    out = str(tmp_path / "mesh.off")
+    oracle.write_off(out, verts, rgb, np.float32(1.0) * s)
+    lines = open(out).read().splitlines()
+    assert lines[0] == "OFF" and lines[1].split()[2] == "0" and int(lines[1].split()[0]) == 3 * int(lines[1].split()[1])
+    assert lines[2:12] == [str(x) for x in g["first_lines"][2:12]]          # same first triangles, same %g formatting
+    assert {tuple(c) for c in rgb.tolist()} == {tuple(c) for c in g["face_colors"].tolist()} == {(50, 168, 141)}
+    ours, cnt = np.unique(verts.reshape(-1, 3).astype(np.int16), axis=0, return_counts=True)
+    gold = {tuple(k): int(c) for k, c in zip(g["uniq"].tolist(), g["counts"].tolist())}
+    common = sum(min(c, gold.get(tuple(k), 0)) for k, c in zip(ours.tolist(), cnt.tolist()))
+    assert common / g["counts"].sum() >= 0.95, common / g["counts"].sum()
+
+
+def test_closure_rejects_even_kernel_and_dilates(oracle):
+    rgba = np.zeros((5 * 4 * 3, 4), np.float32)
+    rgba[1 + 5 * (1 + 4 * 1)] = (10, 20, 30, 1)
+    rgba[2 + 5 * (1 + 4 * 1)] = (50, 60, 70, 1)
+    with pytest.raises(ValueError):
+        oracle.closure(5, 4, 3, rgba, 2)
+    out = oracle.closure(5, 4, 3, rgba, 3)
+    assert (out[:, 3] > 0).sum() == 4 * 3 * 3            # x in 0..3, all y in 0..2 (y = 3 is 2 away), all z
+    assert np.array_equal(out[0 + 5 * (0 + 4 * 0)], (10, 20, 30, 1))          # only the first voxel in reach
+    assert np.array_equal(out[1 + 5 * (0 + 4 * 0)], (30, 40, 50, 1))          # mean of both

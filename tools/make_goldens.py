@@ -250,6 +250,15 @@ def soft_golden():
     with open(p) as f:
         assert f.readline().strip() == "OFF"
         nv, nf, _ = map(int, f.readline().split())
+        verts = np.array([[float(t) for t in f.readline().split()] for _ in range(nv)])
+        faces = [f.readline().split() for _ in range(nf)]
+    # vertices are voxel indices * 0.0028 (scale 1, no translation): keep them as the multiset of integer index triplets
+    idx = np.rint(verts / 0.0028).astype(np.int16)
+    assert np.abs(verts / 0.0028 - idx).max() < 1e-2
+    uniq, counts = np.unique(idx, axis=0, return_counts=True)
+    colors = sorted({tuple(int(c) for c in fc[4:7]) for fc in faces})
+    np.savez_compressed(os.path.join(OUT, "soft_box_1off_vertices.npz"), uniq=uniq, counts=counts.astype(np.int32),
+                        first_lines=np.array(open(p).read().splitlines()[:12]), face_colors=np.array(colors, np.int32))
     json.dump({"source": "Data/box_dataset/generated_models/1.off", "vertices": nv, "faces": nf,
                "command": "-c=5 -z=50 (x=y=100, size=0.0028, carve=1, color=0, postprocessing=true)"},
               open(os.path.join(OUT, "soft_box_1off.json"), "w"), indent=1)
