@@ -69,12 +69,6 @@ int main(int argc, char** argv) {
         vc::reconstructAvgColor(views, model);
         model.handleUnseen();
         const vc::McSummary mc = vc::marchingCubesClassify(model);
-        if (argc > 3) {  // main.cpp:297-303: applyClosure(&model, 3); marchingCubes(&model, scale, translation, 0.5f, outFile)
-            if (vc::applyClosure(&model, 2) != -1) return 4;
-            if (vc::applyClosure(&model, 3) != 0) return 4;
-            const float t[3] = {0.5f, -0.25f, 2.0f};
-            if (!vc::marchingCubes(&model, 1.5f, t, 0.5f, argv[3])) return 4;
-        }
         FILE* o = fopen(argv[2], "wb");
         fwrite(model.voxels.data(), sizeof(Vec4), model.voxels.size(), o);
         fwrite(model.seen_.data(), 1, model.seen_.size(), o);
@@ -84,6 +78,13 @@ int main(int argc, char** argv) {
         fwrite(&nv, 8, 1, o);
         for (const auto& p : perView) fwrite(&p.triangles, 8, 1, o);
         fclose(o);
+        if (argc > 3) {  // main.cpp:297-303: applyClosure(&model, 3); marchingCubes(&model, scale, translation, 0.5f, outFile)
+            if (vc::applyClosure(&model, 2) != -1) return 4;
+            if (vc::applyClosure(&model, 3) != 0) return 4;
+            const float t[3] = {0.5f, -0.25f, 2.0f};
+            if (!vc::marchingCubes(&model, 1.5f, t, 0.5f, argv[3])) return 4;
+        }
+
     } catch (const vc::Error& e) {
         fprintf(stderr, "%s\n", e.what());
         return 3;
