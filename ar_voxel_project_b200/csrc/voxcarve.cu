@@ -453,9 +453,9 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
         bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
         vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
-        const unsigned n_rows = (unsigned)((long long)e->nz * e->g.Y);
-        vc_fill_kernel<<<dim3((n_rows + 7) / 8, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
-            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, n_rows, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, e->reset_pending ? 1 : 0);
+        if (e->nz > 65535) return fail(e, VC_ERR_ARG, "vc_carve: slab of %d planes exceeds the fill grid", e->nz);
+        vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, e->nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
+            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, e->reset_pending ? 1 : 0);
         e->reset_pending = false;
         VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
         const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
