@@ -41,6 +41,7 @@ SIGNATURES = {
     "vc_set_images": (C.c_int, [_P, _P]),
     "vc_reset": (C.c_int, [_P]),
     "vc_carve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vc_carve_download": (C.c_int, [_P, C.c_int32, _P, _P, C.c_uint64]),
     "vc_fast_carve": (C.c_int, [_P, C.c_int32]),
     "vc_color": (C.c_int, [_P, C.c_int32]),
     "vc_mc_classify": (C.c_int, [_P]),

@@ -33,6 +33,8 @@ struct vc_engine {
     long long slab_words = 0, plane_words = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+    cudaStream_t copy_stream = nullptr;   // D2H of finished z-chunks while the next chunk is carving (vc_carve_download)
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_mid = false;
     // volumes
     uint32_t *d_occ_own = nullptr, *d_seen_own = nullptr;    // slab-sized, engine-owned
@@ -252,6 +254,8 @@ void vc_destroy(vc_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evm) cudaEventDestroy(e->evm);
+    for (int c = 0; c < 4; c++) if (e->ev_chunk[c]) cudaEventDestroy(e->ev_chunk[c]);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     {
         std::lock_guard<std::mutex> lk(g_const_mutex);
@@ -392,18 +396,23 @@ int vc_reset(vc_engine* e) {
     return VC_OK;
 }
 
-int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed) {
-    if (!e) return VC_ERR_ARG;
-    if (mode != VC_EXACT && mode != VC_FAST_F32 && mode != VC_EXACT_FLAT) return fail(e, VC_ERR_ARG, "vc_carve: unknown mode %d", mode);
-    if (e->V == 0 || !e->d_mask) return fail(e, VC_ERR_STATE, "vc_carve: views and masks must be set first");
-    if (view_end < 0) view_end = e->V;
-    if (view_begin < 0 || view_begin > view_end || view_end > e->V)
-        return fail(e, VC_ERR_ARG, "vc_carve: bad view range [%d,%d) for V=%d", view_begin, view_end, e->V);
-    if (bind_device(e)) return VC_ERR_CUDA;
-    int rc = ensure_volumes(e);
-    if (rc) return rc;
-    rc = ensure_constants(e);
-    if (rc) return rc;
+// Buffers of the brick classifier, sized for the whole slab (a z-chunk uses a prefix of each).
+static int ensure_brick_buffers(vc_engine* e) {
+    const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+    const long long n_bricks = (long long)nbx * nby * nbz;
+    if (n_bricks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld bricks)", n_bricks);
+    const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER + 1;
+    const long long n_super = (long long)sbx * sby * sbz;
+    if (e->d_bricks) return VC_OK;
+    VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
+    VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
+    VC_CUDA(e, cudaMalloc(&e->d_brick_flags, (size_t)n_bricks));
+    VC_CUDA(e, cudaMalloc(&e->d_super_flags, (size_t)n_super));
+    VC_CUDA(e, cudaMalloc(&e->d_super_list, (size_t)n_super * sizeof(unsigned int)));
+    return VC_OK;
+}
+
+static VcCarveParams carve_params(vc_engine* e, int view_begin, int view_end) {
     const int K = 4;
     VcCarveParams p{};
     p.occ = e->occ_slab(); p.seen = e->seen_slab(); p.mask = e->d_mask;
@@ -416,53 +425,76 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     p.mask_plane = (uint32_t)((size_t)e->H * e->Ww);
     p.v0 = view_begin; p.v1 = view_end;
     p.s = e->g.voxel_size;
-    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
-    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 5, 0, sizeof(unsigned long long), e->stream));
-    const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+    return p;
+}
+
+// VC_EXACT on the planes [zl0, zl1) of the slab (zl0 a multiple of the super-brick height, so bricks sit where they
+// would in a whole-slab pass): classify super-bricks, classify bricks, fill, evaluate the undecided pairs.
+static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bool count, bool fresh, bool record_mid, uint64_t* n_bricks_out) {
+    const long long off = (long long)zl0 * e->plane_words;
+    p.occ += off; p.seen += off;
+    p.z_begin = e->g.z_begin + zl0; p.nz = zl1 - zl0;
+    const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (p.nz + VC_BZ - 1) / VC_BZ;
     const long long n_bricks = (long long)nbx * nby * nbz;
-    if (mode == VC_EXACT) {
-        if (n_bricks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld bricks)", n_bricks);
-        if (!e->d_bricks) VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
-    }
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
     const long long n_super = (long long)sbx * sby * sbz;
-    if (mode == VC_EXACT && !e->d_super) VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
-    if (mode == VC_EXACT && !e->d_brick_flags) {
-        VC_CUDA(e, cudaMalloc(&e->d_brick_flags, (size_t)n_bricks));
-        VC_CUDA(e, cudaMalloc(&e->d_super_flags, (size_t)n_super));
-        VC_CUDA(e, cudaMalloc(&e->d_super_list, (size_t)n_super * sizeof(unsigned int)));
-    }
+    if (p.nz > 65535) return fail(e, VC_ERR_ARG, "vc_carve: slab of %d planes exceeds the fill grid", p.nz);
+    unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length | super-list length, [7] = work counter
+    unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
+    VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
+    VcBrickParams bp{};
+    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
+    bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
+    bp.executed = count ? e->d_scalars + 5 : nullptr;
+    bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = p.nz; bp.z_begin = p.z_begin;
+    bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = p.v0; bp.v1 = p.v1; bp.s = e->g.voxel_size;
+    VcBrickParams sp = bp;  // level 1: super-bricks into the dense array
+    sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
+    bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
+    vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
+    vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
+        p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0);
+    if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
+    const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
+    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
+    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
+    VC_CUDA(e, cudaGetLastError());
+    e->stats.carve_launches += 4;
+    if (n_bricks_out) *n_bricks_out += (uint64_t)n_bricks;
+    return VC_OK;
+}
+
+static int carve_check(vc_engine* e, const char* who, int32_t mode, int32_t& view_begin, int32_t& view_end) {
+    if (mode != VC_EXACT && mode != VC_FAST_F32 && mode != VC_EXACT_FLAT) return fail(e, VC_ERR_ARG, "%s: unknown mode %d", who, mode);
+    if (e->V == 0 || !e->d_mask) return fail(e, VC_ERR_STATE, "%s: views and masks must be set first", who);
+    if (view_end < 0) view_end = e->V;
+    if (view_begin < 0 || view_begin > view_end || view_end > e->V)
+        return fail(e, VC_ERR_ARG, "%s: bad view range [%d,%d) for V=%d", who, view_begin, view_end, e->V);
+    if (bind_device(e)) return VC_ERR_CUDA;
+    int rc = ensure_volumes(e);
+    if (rc) return rc;
+    return ensure_constants(e);
+}
+
+int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed) {
+    if (!e) return VC_ERR_ARG;
+    int rc = carve_check(e, "vc_carve", mode, view_begin, view_end);
+    if (rc) return rc;
+    VcCarveParams p = carve_params(e, view_begin, view_end);
+    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
+    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 5, 0, sizeof(unsigned long long), e->stream));
+    if (mode == VC_EXACT) { rc = ensure_brick_buffers(e); if (rc) return rc; }
     if (mode != VC_EXACT) { rc = materialize_reset(e); if (rc) return rc; }
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     e->have_mid = mode == VC_EXACT;
-    e->stats.bricks_total = mode == VC_EXACT ? (uint64_t)n_bricks : 0;
+    e->stats.bricks_total = 0;
     e->stats.bricks_listed = 0;
     if (mode == VC_EXACT) {
-        unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length | super-list length, [7] = work counter
-        unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
-        VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
-        VcBrickParams bp{};
-        bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
-        bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
-        bp.executed = count_executed ? e->d_scalars + 5 : nullptr;
-        bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
-        bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = view_begin; bp.v1 = view_end; bp.s = e->g.voxel_size;
-        VcBrickParams sp = bp;  // level 1: super-bricks into the dense array
-        sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
-        vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
-        bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-        vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
-        if (e->nz > 65535) return fail(e, VC_ERR_ARG, "vc_carve: slab of %d planes exceeds the fill grid", e->nz);
-        vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, e->nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
-            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, e->reset_pending ? 1 : 0);
+        rc = carve_exact_range(e, p, 0, e->nz, count_executed != 0, e->reset_pending, true, &e->stats.bricks_total);
+        if (rc) return rc;
         e->reset_pending = false;
-        VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
-        const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
-        if (count_executed) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
-        else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
-        VC_CUDA(e, cudaGetLastError());
-        e->stats.carve_launches += 4;
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
         if (rc) return rc;
@@ -486,6 +518,62 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->gathered = false;
     e->have_colors = false;
     e->have_mc = false;
+    return VC_OK;
+}
+
+int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* seen, uint64_t n_words) {
+    if (!e) return VC_ERR_ARG;
+    if (!occupied || !seen) return fail(e, VC_ERR_ARG, "vc_carve_download: null buffer");
+    if (n_words < (uint64_t)e->slab_words) return fail(e, VC_ERR_CAPACITY, "vc_carve_download: buffers hold %llu words, slab has %lld", (unsigned long long)n_words, e->slab_words);
+    int32_t v0 = 0, v1 = -1;
+    int rc = carve_check(e, "vc_carve_download", mode, v0, v1);
+    if (rc) return rc;
+    const int LZ = VC_BZ * VC_SUPER;
+    int n_chunks = e->nz >= 8 * LZ ? 4 : (e->nz >= 2 * LZ ? 2 : 1);
+    if (mode != VC_EXACT) n_chunks = 1;
+    if (n_chunks == 1) {  // nothing to overlap: plain sequence
+        rc = vc_carve(e, mode, 0, -1, 0);
+        if (!rc) rc = vc_download_occupied(e, occupied, n_words);
+        if (!rc) rc = vc_download_seen(e, seen, n_words);
+        return rc;
+    }
+    rc = ensure_brick_buffers(e);
+    if (rc) return rc;
+    if (!e->copy_stream) {
+        VC_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 4; c++) VC_CUDA(e, cudaEventCreateWithFlags(&e->ev_chunk[c], cudaEventDisableTiming));
+    }
+    VcCarveParams p = carve_params(e, v0, v1);
+    const int cz = ((e->nz + n_chunks - 1) / n_chunks + LZ - 1) / LZ * LZ;  // planes per chunk, a multiple of the super-brick height
+    set_mask_window(e, true);
+    VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    e->have_mid = false;
+    e->stats.bricks_total = 0;
+    e->stats.bricks_listed = 0;
+    const bool fresh = e->reset_pending;
+    int c = 0;
+    for (int zl0 = 0; zl0 < e->nz; zl0 += cz, c++) {
+        const int zl1 = zl0 + cz < e->nz ? zl0 + cz : e->nz;
+        rc = carve_exact_range(e, p, zl0, zl1, false, fresh, false, &e->stats.bricks_total);
+        if (rc) return rc;
+        VC_CUDA(e, cudaEventRecord(e->ev_chunk[c], e->stream));
+        VC_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->ev_chunk[c], 0));
+        const long long off = (long long)zl0 * e->plane_words, n = (long long)(zl1 - zl0) * e->plane_words;
+        VC_CUDA(e, cudaMemcpyAsync(occupied + off, e->occ_slab() + off, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+        VC_CUDA(e, cudaMemcpyAsync(seen + off, e->seen_slab() + off, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    }
+    e->reset_pending = false;
+    VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    set_mask_window(e, false);
+    e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)e->V;
+    e->stats.executed_voxel_views = 0;
+    e->stats.brick_corner_views = 0;
+    e->stats.last_carve_ms = -1.0;
+    e->gathered = false;
+    e->have_colors = false;
+    e->have_mc = false;
+    VC_CUDA(e, cudaStreamSynchronize(e->copy_stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
     return VC_OK;
 }
 

@@ -142,6 +142,16 @@ class VoxelEngine:
     def carve(self, mode=L.VC_EXACT, view_begin=0, view_end=-1, count_executed=False):
         self._check(self._lib.vc_carve(self._h, mode, view_begin, view_end, int(bool(count_executed))))
 
+    def carve_download(self, out_occ=None, out_seen=None, mode=L.VC_EXACT):
+        """carve all views and download both volumes, D2H of finished z-chunks overlapped with the carving of the next"""
+        n = (self.z_end - self.z_begin) * self.Y * self.Wx
+        if out_occ is None:
+            out_occ, out_seen = np.empty(self.slab_shape, np.uint32), np.empty(self.slab_shape, np.uint32)
+        a, ka = _host_ptr(out_occ, np.uint32, n * 4, "occupied buffer")
+        b, kb = _host_ptr(out_seen, np.uint32, n * 4, "seen buffer")
+        self._check(self._lib.vc_carve_download(self._h, mode, C.c_void_p(a), C.c_void_p(b), n))
+        return out_occ, out_seen
+
     def fast_carve(self, mode=L.VC_EXACT):
         self._check(self._lib.vc_fast_carve(self._h, mode))
 

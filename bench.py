@@ -230,7 +230,7 @@ def run_ours(args):
     clk["sampled_over"] = f"{args.warmup} warm-up + {args.steps} timed + {n_tail} identical untimed steps"
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = allmax(float(np.mean(step_ms)))
-    launches = 3 * args.steps  # vc_reset_kernel + vc_brick_classify_kernel + vc_carve_bricks per step
+    launches = 4 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_fill_kernel (absorbs the reset), vc_carve_bricks per step
 
     # carve-kernel-only time (events inside vc_carve) and executed voxel-views (separate, untimed counting pass)
     kt, ct = [], []
@@ -309,9 +309,7 @@ def run_ours(args):
                 else:
                     eng.set_masks_bgr(bgr, sync=False)
                 eng.reset()
-                eng.carve(A._lib.VC_EXACT)
-                eng.download_occupied(out_occ)
-                eng.download_seen(out_seen)
+                eng.carve_download(out_occ, out_seen)   # carve + D2H of both volumes, z-chunks overlapped
             for _ in range(2):
                 one()
             barrier()
@@ -323,13 +321,14 @@ def run_ours(args):
 
         s_bits = e2e_run(True)
         s_bgr = e2e_run(False)
-        # kernels per e2e step: [pack_bgr], sat_rows, sat_cols, reset, classify, carve_bricks
+        # kernels per e2e step: [pack_bgr] + 3 SAT passes + 4 z-chunks x (2 classify + fill + carve_bricks)
         e2e = {"value": nominal_total / s_bits, "unit": UNIT, "h2d_bytes_per_step": int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bits * 1e3,
-               "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory", "gpu_launches": 5 * args.steps}
+               "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory",
+               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download", "gpu_launches": 19 * args.steps}
         e2e_bgr = {"value": nominal_total / s_bgr, "unit": UNIT, "h2d_bytes_per_step": int(bgr.numel() + w.P.nbytes + w.M.nbytes),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bgr * 1e3,
-                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 6 * args.steps}
+                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 20 * args.steps}
         eng.set_masks_bits(w.mask_bits)
 
     out = None

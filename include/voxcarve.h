@@ -111,6 +111,10 @@ VC_EXPORT int vc_reset(vc_engine* e);
  * engine's slab; accumulates into the current volumes (call vc_reset first for a fresh Model).
  * view_end < 0 means V. count_executed != 0 also fills vc_stats.executed_voxel_views (slower). */
 VC_EXPORT int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed);
+/* carve() over all views followed by the download of both volumes into HOST buffers, as the shim needs them.  The slab is
+ * carved in z-chunks and every finished chunk is copied on a second stream while the next one is carving, so the
+ * PCIe transfer overlaps the kernels.  Same result as vc_carve + vc_download_occupied + vc_download_seen. */
+VC_EXPORT int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* seen, uint64_t n_words);
 /* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): starts from the Model constructor state (it resets the
  * volumes itself) and needs the whole grid on this engine. */
 VC_EXPORT int vc_fast_carve(vc_engine* e, int32_t mode);

@@ -75,6 +75,12 @@ class Engine {
     }
     void reset() { check(vc_reset(h_)); }
     void carve(int mode = VC_EXACT, int v0 = 0, int v1 = -1) { check(vc_carve(h_, mode, v0, v1, 0)); }
+    // carve all views + download both volumes, the D2H of finished z-chunks overlapped with the carving of the next
+    void carveDownload(std::vector<uint32_t>& occ, std::vector<uint32_t>& seen, int mode = VC_EXACT) {
+        occ.resize(words_);
+        seen.resize(words_);
+        check(vc_carve_download(h_, mode, occ.data(), seen.data(), words_));
+    }
     void fastCarve(int mode = VC_EXACT) { check(vc_fast_carve(h_, mode)); }
     void color(int mode) { check(vc_color(h_, mode)); }
     McSummary mcClassify() {
@@ -187,16 +193,19 @@ void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = fals
     std::cout << "LOG - VC: starting carving process (version 1)." << std::endl;
     Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
     e.setViews(views, false);
+    std::vector<uint32_t> occ, seen;
     if (intermediateMeshes) {
         for (int i = 0; i < views.V; i++) {
             e.carve(VC_EXACT, i, i + 1);
             const McSummary s = e.mcClassify();
             if (perView) perView->push_back(s);
         }
+        occ = e.occupied();
+        seen = e.seen();
     } else {
-        e.carve();
+        e.carveDownload(occ, seen);
     }
-    detail::applyCarve(model, e.occupied(), e.seen());
+    detail::applyCarve(model, occ, seen);
     std::cout << "LOG - VC: carving complete." << std::endl;
 }
 

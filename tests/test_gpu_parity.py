@@ -464,3 +464,24 @@ def test_soft_golden_box_mesh_on_device(A, oracle, golden):
         verts, rgb = e.mc_mesh(0.5)
     assert abs(len(verts) - soft["faces"]) / soft["faces"] < 0.005
     assert (rgb == (50, 168, 141)).all()   # 1.off faces are all MODEL_COLOR
+
+
+@pytest.mark.parametrize("dims", [(64, 40, 300), (96, 33, 70), (40, 20, 31)])
+def test_carve_download_chunked_equals_plain(A, oracle, dims):
+    """vc_carve_download (z-chunks, D2H overlapped with the next chunk) == vc_carve + downloads == oracle slab"""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = dims
+    w = Workload(max(dims), 7, 320, 240, seed=8, dims=dims)
+    with A.VoxelEngine(X, Y, Z, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        e.carve()
+        occ, seen = e.download_occupied(), e.download_seen()
+        for _ in range(2):
+            e.reset()
+            o2, s2 = e.carve_download()
+            assert np.array_equal(o2, occ) and np.array_equal(s2, seen)
+        e.carve_download(o2, s2)  # accumulate on the carved state: nothing changes
+        assert np.array_equal(o2, occ) and np.array_equal(s2, seen)
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=Z // 2, z1=Z // 2 + 3)
+    assert np.array_equal(occ[Z // 2:Z // 2 + 3], ro) and np.array_equal(seen[Z // 2:Z // 2 + 3], rs)
