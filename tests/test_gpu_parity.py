@@ -485,3 +485,23 @@ def test_carve_download_chunked_equals_plain(A, oracle, dims):
         assert np.array_equal(o2, occ) and np.array_equal(s2, seen)
     ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=Z // 2, z1=Z // 2 + 3)
     assert np.array_equal(occ[Z // 2:Z // 2 + 3], ro) and np.array_equal(seen[Z // 2:Z // 2 + 3], rs)
+
+
+def test_config4_1024cubed_full_size_properties(A, oracle):
+    """BASELINE configs[3] at full size (1024^3 x 72 views x 1920x1080) on one GPU: VC_EXACT == VC_EXACT_FLAT bit for bit,
+    carved => seen, and three 2-plane slabs against the oracle."""
+    from ar_voxel_project_b200.synth import Workload, CONFIGS
+    w = Workload(**CONFIGS["C4"])
+    with A.VoxelEngine(1024, 1024, 1024, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        occ, seen = e.carve_download()
+        n_occ, n_seen = e.count_occupied()
+        e.reset()
+        e.carve(2)
+        assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
+    assert ((~occ) & (~seen)).max() == 0
+    assert 0.02 < n_occ / 1024 ** 3 < 0.25 and n_seen <= 1024 ** 3
+    for z0 in (0, 511, 1022):
+        ro, rs = oracle.carve(1024, 1024, 1024, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z0 + 2, nthreads=0)
+        assert np.array_equal(occ[z0:z0 + 2], ro) and np.array_equal(seen[z0:z0 + 2], rs)
