@@ -96,5 +96,26 @@ inline void reconstructAvgColor(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, Mode
     vc::reconstructAvgColor(vc::cachedViews(cameraMatrix, distCoeffs, images, masks, true), model);
     Benchmark::GetInstance().LogColoring(false);
 }
+
+// Optional: also replace applyClosure (Postprocessing3d.cpp) and marchingCubes (MarchingCubes.cpp) — define
+// VOXCARVE_SHIM_REPLACE_POSTPROCESSING and drop those two .cpp files from the build as well. The prototypes (with their
+// default arguments) stay in Postprocessing3d.h:10 and MarchingCubes.h:596.
+#ifdef VOXCARVE_SHIM_REPLACE_POSTPROCESSING
+#include "MarchingCubes.h"
+#include "Postprocessing3d.h"
+inline int applyClosure(Model* model, int kernelSize) {
+    Benchmark::GetInstance().LogPostProcessing(true);
+    const int rc = vc::applyClosure(model, kernelSize);
+    Benchmark::GetInstance().LogPostProcessing(false);
+    return rc;
+}
+inline bool marchingCubes(Model* model, float scale, Vector3f translation, float threshold, std::string outFileName) {
+    Benchmark::GetInstance().LogMarchingCubes(true);  // the reference stops this clock before writing the file (MarchingCubes.cpp:19)
+    const float t[3] = {translation.x(), translation.y(), translation.z()};
+    const bool ok = vc::marchingCubes(model, scale, t, threshold, outFileName);
+    Benchmark::GetInstance().LogMarchingCubes(false);
+    return ok;
+}
+#endif
 #endif  // VOXCARVE_SHIM_ENABLED
 #endif  // VOXCARVE_SHIM_HPP
