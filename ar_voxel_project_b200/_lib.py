@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libvoxcarve.so")
 VC_OK, VC_ERR_ARG, VC_ERR_CUDA, VC_ERR_STATE, VC_ERR_CAPACITY = 0, 1, 2, 3, 4
 VC_EXACT, VC_FAST_F32, VC_EXACT_FLAT = 0, 1, 2
 VC_COLOR_CLOSEST, VC_COLOR_AVG = 1, 2
-VC_MASK_BITS, VC_MASK_BGR8 = 0, 1
+VC_MASK_BITS, VC_MASK_BGR8, VC_MASK_BGR8_RAW = 0, 1, 2
 
 
 class GridDesc(C.Structure):
@@ -39,6 +39,11 @@ SIGNATURES = {
     "vc_set_views": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vc_set_masks": (C.c_int, [_P, _P, C.c_int32]),
     "vc_set_images": (C.c_int, [_P, _P]),
+    "vc_set_calibration": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "vc_set_images_raw": (C.c_int, [_P, _P]),
+    "vc_download_masks": (C.c_int, [_P, _P]),
+    "vc_download_images": (C.c_int, [_P, _P]),
+    "vc_undistort_bgr": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P]),
     "vc_reset": (C.c_int, [_P]),
     "vc_carve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vc_carve_download": (C.c_int, [_P, C.c_int32, _P, _P, C.c_uint64]),

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,6 +26,8 @@ ConstOwner g_const_owner[64];
 unsigned long long g_next_uid = 1;
 
 }  // namespace
+
+static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream);
 
 struct vc_engine {
     vc_grid_desc g{};
@@ -75,6 +78,8 @@ struct vc_engine {
     uint32_t* d_mesh_rgb = nullptr;
     unsigned long long n_mesh_tris = 0;
     bool have_dense = false, have_mesh = false;
+    bool have_calib = false;
+    double calib_K[9] = {0}, calib_dist[8] = {0};
     vc_stats stats{};
     std::string err;
 
@@ -319,7 +324,8 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
     if (!e) return VC_ERR_ARG;
     if (!masks) return fail(e, VC_ERR_ARG, "vc_set_masks: null buffer");
     if (e->V == 0) return fail(e, VC_ERR_STATE, "vc_set_masks: call vc_set_views first");
-    if (format != VC_MASK_BITS && format != VC_MASK_BGR8) return fail(e, VC_ERR_ARG, "vc_set_masks: unknown format %d", format);
+    if (format != VC_MASK_BITS && format != VC_MASK_BGR8 && format != VC_MASK_BGR8_RAW) return fail(e, VC_ERR_ARG, "vc_set_masks: unknown format %d", format);
+    if (format == VC_MASK_BGR8_RAW && !e->have_calib) return fail(e, VC_ERR_STATE, "vc_set_masks: raw masks need vc_set_calibration first");
     if (bind_device(e)) return VC_ERR_CUDA;
     if (!e->d_mask) VC_CUDA(e, cudaMalloc(&e->d_mask, e->mask_bytes));
     if (format == VC_MASK_BITS) {
@@ -334,6 +340,15 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
         }
         uint8_t* d_tmp = e->d_bgr_tmp;
         VC_CUDA(e, cudaMemcpyAsync(d_tmp, masks, bytes, cudaMemcpyHostToDevice, e->stream));
+        if (format == VC_MASK_BGR8_RAW) {  // cv::undistort(mask, undist_mask, cameraMatrix, distCoeffs) (VoxelCarving.cpp:36)
+            uint8_t* d_und = nullptr;
+            VC_CUDA(e, cudaMalloc(&d_und, bytes));
+            cudaError_t us = undistort_device(d_tmp, d_und, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream);
+            if (us == cudaSuccess) us = cudaMemcpyAsync(d_tmp, d_und, bytes, cudaMemcpyDeviceToDevice, e->stream);
+            if (us == cudaSuccess) us = cudaStreamSynchronize(e->stream);
+            cudaFree(d_und);
+            if (us != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_set_masks: undistort failed: %s", cudaGetErrorString(us));
+        }
         const long long n_rows = (long long)e->V * e->H, warps = n_rows * e->Ww;
         const long long blocks = (warps * 32 + 255) / 256;
         vc_pack_bgr_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(d_tmp, e->d_mask, e->W, e->Ww, n_rows);
@@ -365,6 +380,61 @@ int vc_set_images(vc_engine* e, const uint8_t* images_bgr) {
     return VC_OK;
 }
 
+// 3x3 inverse by Gaussian elimination with partial pivoting on [A | I] (cv::invert, DECOMP_LU), f64, no FMA
+static void inv3x3_lu(const double* A, double* inv) {
+    volatile double a[3][3], b[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { a[i][j] = A[i * 3 + j]; b[i][j] = i == j; }
+    for (int i = 0; i < 3; i++) {
+        int k = i;
+        for (int j = i + 1; j < 3; j++) if (fabs(a[j][i]) > fabs(a[k][i])) k = j;
+        if (k != i) for (int j = 0; j < 3; j++) { double t = a[i][j]; a[i][j] = a[k][j]; a[k][j] = t; t = b[i][j]; b[i][j] = b[k][j]; b[k][j] = t; }
+        const double d = -1 / a[i][i];
+        for (int j = i + 1; j < 3; j++) {
+            const double alpha = a[j][i] * d;
+            for (int c = i + 1; c < 3; c++) { const double t = alpha * a[i][c]; a[j][c] = a[j][c] + t; }
+            for (int c = 0; c < 3; c++) { const double t = alpha * b[i][c]; b[j][c] = b[j][c] + t; }
+        }
+    }
+    for (int i = 2; i >= 0; i--)
+        for (int j = 0; j < 3; j++) {
+            double s = b[i][j];
+            for (int k = i + 1; k < 3; k++) { const double t = a[i][k] * b[k][j]; s = s - t; }
+            b[i][j] = s / a[i][i];
+        }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) inv[i * 3 + j] = b[i][j];
+}
+
+// device-to-device cv::undistort of n 8UC3 images on `stream`
+static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream) {
+    int stripe = (1 << 12) / (W > 1 ? W : 1);
+    if (stripe < 1) stripe = 1;
+    if (stripe > H) stripe = H;
+    const int n_stripes = (H + stripe - 1) / stripe;
+    std::vector<double> ir((size_t)n_stripes * 9);
+    for (int sidx = 0; sidx < n_stripes; sidx++) {
+        double Ar[9];
+        memcpy(Ar, K, sizeof Ar);
+        Ar[5] = K[5] - (double)(sidx * stripe);
+        inv3x3_lu(Ar, &ir[(size_t)sidx * 9]);
+    }
+    double* d_ir = nullptr;
+    cudaError_t s = cudaMalloc(&d_ir, ir.size() * sizeof(double));
+    if (s != cudaSuccess) return s;
+    s = cudaMemcpyAsync(d_ir, ir.data(), ir.size() * sizeof(double), cudaMemcpyHostToDevice, stream);
+    if (s == cudaSuccess) s = cudaStreamSynchronize(stream);  // `ir` is a local
+    if (s == cudaSuccess) {
+        VcUndistortParams p{};
+        p.src = d_src; p.dst = d_dst; p.ir = d_ir; p.W = W; p.H = H; p.n = n; p.stripe = stripe;
+        p.fx = K[0]; p.fy = K[4]; p.u0 = K[2]; p.v0 = K[5];
+        p.k1 = dist8[0]; p.k2 = dist8[1]; p.p1 = dist8[2]; p.p2 = dist8[3]; p.k3 = dist8[4]; p.k4 = dist8[5]; p.k5 = dist8[6]; p.k6 = dist8[7];
+        vc_undistort_kernel<<<dim3((W + 255) / 256, H, n), 256, 0, stream>>>(p);
+        s = cudaGetLastError();
+        if (s == cudaSuccess) s = cudaStreamSynchronize(stream);
+    }
+    cudaFree(d_ir);
+    return s;
+}
+
 // engine-owned volumes are allocated on first use (a planning engine, vc_plan_slabs, never needs them)
 static int ensure_volumes(vc_engine* e) {
     if (e->d_occ_full || e->d_occ_own) return VC_OK;
@@ -384,6 +454,71 @@ static int materialize_reset(vc_engine* e) {
     vc_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), n, e->Wx, e->g.X);
     VC_CUDA(e, cudaGetLastError());
     e->reset_pending = false;
+    return VC_OK;
+}
+
+int vc_set_calibration(vc_engine* e, const double K[9], const double* dist, int32_t n_dist) {
+    if (!e) return VC_ERR_ARG;
+    if (!K || !dist) return fail(e, VC_ERR_ARG, "vc_set_calibration: null argument");
+    if (n_dist != 4 && n_dist != 5 && n_dist != 8) return fail(e, VC_ERR_ARG, "vc_set_calibration: %d distortion coefficients (need 4, 5 or 8)", n_dist);
+    for (int i = 0; i < 9; i++) e->calib_K[i] = K[i];
+    for (int i = 0; i < 8; i++) e->calib_dist[i] = i < n_dist ? dist[i] : 0.0;
+    e->have_calib = true;
+    return VC_OK;
+}
+
+int vc_set_images_raw(vc_engine* e, const uint8_t* images_bgr) {
+    if (!e) return VC_ERR_ARG;
+    if (!images_bgr) return fail(e, VC_ERR_ARG, "vc_set_images_raw: null buffer");
+    if (e->V == 0) return fail(e, VC_ERR_STATE, "vc_set_images_raw: call vc_set_views first");
+    if (!e->have_calib) return fail(e, VC_ERR_STATE, "vc_set_images_raw: needs vc_set_calibration first");
+    if (bind_device(e)) return VC_ERR_CUDA;
+    const size_t bytes = (size_t)e->V * e->H * e->W * 3;
+    if (!e->d_images) VC_CUDA(e, cudaMalloc(&e->d_images, bytes));
+    uint8_t* d_raw = nullptr;
+    VC_CUDA(e, cudaMalloc(&d_raw, bytes));
+    cudaError_t s = cudaMemcpyAsync(d_raw, images_bgr, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (s == cudaSuccess) s = undistort_device(d_raw, e->d_images, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream);  // ColorReconstruction.h:23
+    cudaFree(d_raw);
+    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_set_images_raw: %s", cudaGetErrorString(s));
+    return VC_OK;
+}
+
+int vc_download_masks(vc_engine* e, uint32_t* bits) {
+    if (!e) return VC_ERR_ARG;
+    if (!bits) return fail(e, VC_ERR_ARG, "vc_download_masks: null buffer");
+    if (!e->d_mask) return fail(e, VC_ERR_STATE, "vc_download_masks: no masks set");
+    if (bind_device(e)) return VC_ERR_CUDA;
+    VC_CUDA(e, cudaMemcpyAsync(bits, e->d_mask, e->mask_bytes, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return VC_OK;
+}
+
+int vc_download_images(vc_engine* e, uint8_t* images_bgr) {
+    if (!e) return VC_ERR_ARG;
+    if (!images_bgr) return fail(e, VC_ERR_ARG, "vc_download_images: null buffer");
+    if (!e->d_images) return fail(e, VC_ERR_STATE, "vc_download_images: no images set");
+    if (bind_device(e)) return VC_ERR_CUDA;
+    VC_CUDA(e, cudaMemcpyAsync(images_bgr, e->d_images, (size_t)e->V * e->H * e->W * 3, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return VC_OK;
+}
+
+int vc_undistort_bgr(int32_t device, int32_t n, int32_t W, int32_t H, const uint8_t* src, const double K[9], const double* dist, int32_t n_dist, uint8_t* dst) {
+    if (!src || !dst || !K || !dist || n < 1 || W < 1 || H < 1) return fail(nullptr, VC_ERR_ARG, "vc_undistort_bgr: bad argument");
+    if (n_dist != 4 && n_dist != 5 && n_dist != 8) return fail(nullptr, VC_ERR_ARG, "vc_undistort_bgr: %d distortion coefficients (need 4, 5 or 8)", n_dist);
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, VC_ERR_CUDA, "vc_undistort_bgr: no CUDA device %d; this engine has no CPU fallback", device); }
+    double d8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_dist; i++) d8[i] = dist[i];
+    const size_t bytes = (size_t)n * H * W * 3;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    cudaError_t s = cudaMalloc(&d_src, bytes);
+    if (s == cudaSuccess) s = cudaMalloc(&d_dst, bytes);
+    if (s == cudaSuccess) s = cudaMemcpy(d_src, src, bytes, cudaMemcpyHostToDevice);
+    if (s == cudaSuccess) s = undistort_device(d_src, d_dst, n, W, H, K, d8, 0);
+    if (s == cudaSuccess) s = cudaMemcpy(dst, d_dst, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_src); cudaFree(d_dst);
+    if (s != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_undistort_bgr: %s", cudaGetErrorString(s));
     return VC_OK;
 }
 

@@ -130,6 +130,32 @@ class VoxelEngine:
         self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BITS))
         self._keep = [keep]
 
+    def set_calibration(self, K, dist):
+        """camera matrix (3x3) and distortion coefficients (4, 5 or 8) for the on-device cv::undistort"""
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+        self._check(self._lib.vc_set_calibration(self._h, C.c_void_p(K.ctypes.data), C.c_void_p(d.ctypes.data), len(d)))
+
+    def set_masks_raw(self, bgr):
+        """distorted 8UC3 masks as cv::imread delivers them; undistorted (VoxelCarving.cpp:36) and packed on the device"""
+        addr, keep = _host_ptr(bgr, np.uint8, self.V * self.H * self.W * 3, "raw mask bgr")
+        self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BGR8_RAW))
+        self.synchronize()
+
+    def set_images_raw(self, images_bgr):
+        addr, keep = _host_ptr(images_bgr, np.uint8, self.V * self.H * self.W * 3, "raw images bgr")
+        self._check(self._lib.vc_set_images_raw(self._h, C.c_void_p(addr)))
+
+    def download_masks(self):
+        out = np.empty((self.V, self.H, (self.W + 31) // 32), np.uint32)
+        self._check(self._lib.vc_download_masks(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def download_images(self):
+        out = np.empty((self.V, self.H, self.W, 3), np.uint8)
+        self._check(self._lib.vc_download_images(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
     def set_images(self, images_bgr):
         addr, keep = _host_ptr(images_bgr, np.uint8, self.V * self.H * self.W * 3, "images bgr")
         self._check(self._lib.vc_set_images(self._h, C.c_void_p(addr)))
@@ -275,3 +301,21 @@ def selftest(which, n, seed=0, device=0):
     if rc != L.VC_OK:
         raise VoxCarveError(rc, lib.vc_last_error(None).decode())
     return a.value, b.value
+
+
+def undistort_bgr(images_bgr, K, dist, device=0):
+    """cv::undistort of uint8[n,H,W,3] (or [H,W,3]) on the GPU, bit-exact with OpenCV's 8UC3 path"""
+    lib = L.load()
+    img = np.ascontiguousarray(images_bgr, np.uint8)
+    single = img.ndim == 3
+    if single:
+        img = img[None]
+    n, H, W, _ = img.shape
+    Kc = np.ascontiguousarray(K, np.float64).reshape(9)
+    d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+    out = np.empty_like(img)
+    rc = lib.vc_undistort_bgr(int(device), n, W, H, C.c_void_p(img.ctypes.data), C.c_void_p(Kc.ctypes.data), C.c_void_p(d.ctypes.data), len(d),
+                              C.c_void_p(out.ctypes.data))
+    if rc != L.VC_OK:
+        raise VoxCarveError(rc, lib.vc_last_error(None).decode())
+    return out[0] if single else out

@@ -65,7 +65,7 @@ typedef struct vc_grid_desc {
 enum vc_carve_mode { VC_EXACT = 0, VC_FAST_F32 = 1, VC_EXACT_FLAT = 2 };
 /* values of the reference's -color flag (main.cpp:30,278-288) */
 enum vc_color_mode { VC_COLOR_CLOSEST = 1, VC_COLOR_AVG = 2 };
-enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1 };
+enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1, VC_MASK_BGR8_RAW = 2 /* distorted: undistorted on the device, needs vc_set_calibration */ };
 
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
@@ -103,6 +103,17 @@ VC_EXPORT int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const 
 VC_EXPORT int vc_set_masks(vc_engine* e, const void* masks, int32_t format);
 /* Undistorted colour images 8UC3 BGR (ColorReconstruction.h:23), uint8[V][H][W][3], HOST memory. */
 VC_EXPORT int vc_set_images(vc_engine* e, const uint8_t* images_bgr);
+/* Camera calibration for the on-device cv::undistort (VoxelCarving.cpp:36; ColorReconstruction.h:23): K = 3x3 camera matrix,
+ * dist = (k1 k2 p1 p2 [k3 [k4 k5 k6]]) as read from cameracalibration.yml (aruco_samples_utility.hpp:9-16), n_dist in {4,5,8}. */
+VC_EXPORT int vc_set_calibration(vc_engine* e, const double K[9], const double* dist, int32_t n_dist);
+/* Raw (distorted) colour images as cv::imread delivers them; undistorted on the device, bit-exact with cv::undistort. */
+VC_EXPORT int vc_set_images_raw(vc_engine* e, const uint8_t* images_bgr);
+/* what the device holds after vc_set_masks / vc_set_images*: bit masks uint32[V][H][ceil(W/32)], images uint8[V][H][W][3] */
+VC_EXPORT int vc_download_masks(vc_engine* e, uint32_t* bits);
+VC_EXPORT int vc_download_images(vc_engine* e, uint8_t* images_bgr);
+/* cv::undistort of n 8UC3 images, HOST in / HOST out, on `device` (utility; the engine paths above keep the data on the GPU). */
+VC_EXPORT int vc_undistort_bgr(int32_t device, int32_t n, int32_t W, int32_t H, const uint8_t* src, const double K[9], const double* dist,
+                               int32_t n_dist, uint8_t* dst);
 
 /* ---- the hot path ---------------------------------------------------------------- */
 /* Model constructor state (Model.cpp:9-14): every voxel occupied, none seen. */

@@ -43,6 +43,8 @@ def lib():
         L.vo_mc_classify.argtypes = [C.c_int] * 3 + [u32p, u8p, u64p, u64p, u64p]
         L.vo_pixel_of.argtypes = [f32p] + [C.c_int] * 3 + [C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), f32p]
         L.vo_max_threads.restype = C.c_int
+        L.vo_undistort.argtypes = [C.c_int, C.c_int, u8p, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"),
+                                   np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int, u8p]
         L.vo_closure.argtypes = [C.c_int] * 4 + [f32p, f32p]
         L.vo_marching_cubes.argtypes = [C.c_int] * 3 + [f32p, C.c_float, np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS"), f32p, u32p, C.c_uint64]
         L.vo_marching_cubes.restype = C.c_uint64
@@ -197,3 +199,15 @@ def dense_model(X, Y, Z, occ_words, seen_words=None, color_idx=None, color_rgbn=
     if seen_words is not None:
         rgba[~unpack(seen_words, X).reshape(-1)] = (204, 0, 0, 1)
     return rgba
+
+
+def undistort(img_bgr, K, dist):
+    """cv::undistort of an 8UC3 image (VoxelCarving.cpp:36) -> uint8[H,W,3]"""
+    img = np.ascontiguousarray(img_bgr, np.uint8)
+    H, W = img.shape[:2]
+    d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+    out = np.empty_like(img)
+    rc = lib().vo_undistort(W, H, img, np.ascontiguousarray(K, np.float64).reshape(9), d, len(d), out)
+    if rc != 0:
+        raise ValueError("distortion vector must have 4, 5 or 8 coefficients")
+    return out

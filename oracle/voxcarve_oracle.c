@@ -437,3 +437,80 @@ VO_API int vo_write_off(const char* path, uint64_t ntris, const float* verts, co
     fclose(f);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * cv::undistort as the reference calls it (VoxelCarving.cpp:36,86,89; ColorReconstruction.h:23,26): 8UC3 image,
+ * camera matrix K (3x3 f64), distortion (k1 k2 p1 p2 [k3 [k4 k5 k6]]).  The algorithm lives in OpenCV (un-vendored,
+ * un-pinned by the reference; pinned here to cv2 4.13.0 through tests/golden/undistort_kat.npz):
+ *   stripes of min(max(1, 4096/cols), rows) rows; per stripe the new camera matrix is K with cy - y0 and the map is
+ *   initUndistortRectifyMap(K, dist, I, K') in f64:  (x, y) = K'^-1 (j, i, 1);  radial/tangential model;  (u, v) = K (xd, yd, 1);
+ *   fixed point: iu = round_half_even(u * 32), sx = iu >> 5, fx = iu & 31 (same for v);
+ *   remap INTER_LINEAR, BORDER_CONSTANT(0): out = (sum_taps src * w + 2^14) >> 15 with w = (32-fx|fx)(32-fy|fy) * 32.
+ * ---------------------------------------------------------------------------------------------- */
+static void inv3x3_lu(const double* A, double* inv) { /* Gaussian elimination with partial pivoting on [A | I], as cv::invert(DECOMP_LU) */
+    double a[3][3], b[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { a[i][j] = A[i * 3 + j]; b[i][j] = i == j; }
+    for (int i = 0; i < 3; i++) {
+        int k = i;
+        for (int j = i + 1; j < 3; j++) if (fabs(a[j][i]) > fabs(a[k][i])) k = j;
+        if (k != i) for (int j = 0; j < 3; j++) { double t = a[i][j]; a[i][j] = a[k][j]; a[k][j] = t; t = b[i][j]; b[i][j] = b[k][j]; b[k][j] = t; }
+        double d = -1 / a[i][i];
+        for (int j = i + 1; j < 3; j++) {
+            double alpha = a[j][i] * d;
+            for (int c = i + 1; c < 3; c++) a[j][c] += alpha * a[i][c];
+            for (int c = 0; c < 3; c++) b[j][c] += alpha * b[i][c];
+        }
+    }
+    for (int i = 2; i >= 0; i--)
+        for (int j = 0; j < 3; j++) {
+            double s = b[i][j];
+            for (int k = i + 1; k < 3; k++) s -= a[i][k] * b[k][j];
+            b[i][j] = s / a[i][i];
+        }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) inv[i * 3 + j] = b[i][j];
+}
+
+VO_API int vo_undistort(int W, int H, const uint8_t* src, const double* K, const double* dist, int n_dist, uint8_t* dst) {
+    if (n_dist != 4 && n_dist != 5 && n_dist != 8) return -1;
+    double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_dist; i++) k[i] = dist[i];
+    const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3], k3 = k[4], k4 = k[5], k5 = k[6], k6 = k[7];
+    const double fx = K[0], fy = K[4], u0 = K[2], v0 = K[5];
+    int stripe0 = (1 << 12) / (W > 1 ? W : 1);
+    if (stripe0 < 1) stripe0 = 1;
+    if (stripe0 > H) stripe0 = H;
+    for (int y0 = 0; y0 < H; y0 += stripe0) {
+        int n = stripe0 < H - y0 ? stripe0 : H - y0;
+        double Ar[9], ir[9];
+        memcpy(Ar, K, sizeof Ar);
+        Ar[5] = v0 - y0;
+        inv3x3_lu(Ar, ir);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < W; j++) {
+                double _x = (i * ir[1] + ir[2]) + j * ir[0], _y = (i * ir[4] + ir[5]) + j * ir[3], _w = (i * ir[7] + ir[8]) + j * ir[6];
+                double w = 1. / _w, x = _x * w, y = _y * w;
+                double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+                double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+                double xd = (x * kr + p1 * _2xy) + p2 * (r2 + 2 * x2);
+                double yd = (y * kr + p1 * (r2 + 2 * y2)) + p2 * _2xy;
+                double u = fx * xd + u0, v = fy * yd + v0;
+                double ru = nearbyint(u * 32), rv = nearbyint(v * 32); /* cvRound: round half to even, saturating */
+                int iu = ru >= 2147483647.0 ? INT32_MAX : (ru <= -2147483648.0 || ru != ru ? INT32_MIN : (int)ru);
+                int iv = rv >= 2147483647.0 ? INT32_MAX : (rv <= -2147483648.0 || rv != rv ? INT32_MIN : (int)rv);
+                int sx = iu >> 5, sy = iv >> 5, ax = iu & 31, ay = iv & 31;
+                int wt[4] = {(32 - ax) * (32 - ay) * 32, ax * (32 - ay) * 32, (32 - ax) * ay * 32, ax * ay * 32};
+                uint8_t* o = dst + ((size_t)(y0 + i) * W + j) * 3;
+                for (int c = 0; c < 3; c++) {
+                    int acc = 0;
+                    for (int t = 0; t < 4; t++) {
+                        int xx = sx + (t & 1), yy = sy + (t >> 1);
+                        int val = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? src[((size_t)yy * W + xx) * 3 + c] : 0;
+                        acc += val * wt[t];
+                    }
+                    acc = (acc + (1 << 14)) >> 15;
+                    o[c] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+                }
+            }
+    }
+    return 0;
+}

@@ -505,3 +505,33 @@ def test_config4_1024cubed_full_size_properties(A, oracle):
     for z0 in (0, 511, 1022):
         ro, rs = oracle.carve(1024, 1024, 1024, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z0 + 2, nthreads=0)
         assert np.array_equal(occ[z0:z0 + 2], ro) and np.array_equal(seen[z0:z0 + 2], rs)
+
+
+def test_device_undistort_matches_cv2_kat_and_raw_mask_path(A, oracle, golden):
+    """SURVEY §8f-4: cv::undistort on the device. (1) vc_undistort_bgr == cv2 4.13.0 outputs byte for byte on every KAT case;
+    (2) raw (distorted) masks / images handed to the engine give the same bit masks / images as undistorting with the oracle."""
+    import cv2  # PNG decode of the fixture only
+    from ar_voxel_project_b200.engine import undistort_bgr
+    from ar_voxel_project_b200.synth import pack_bits
+    z = golden("undistort_kat.npz")
+    for n in z["names"]:
+        src, dst = cv2.imdecode(z[f"{n}_src"], 1), cv2.imdecode(z[f"{n}_dst"], 1)
+        assert np.array_equal(undistort_bgr(src, z[f"{n}_K"], z[f"{n}_dist"]), dst), n
+    raw = np.stack([cv2.imdecode(z["box_mask0000_src"], 1), cv2.imdecode(z["human_mask_5_src"], 1)])
+    img = np.stack([cv2.imdecode(z["box_image0003_src"], 1)] * 2)
+    K, dist = z["box_mask0000_K"], z["box_mask0000_dist"]
+    und = np.stack([oracle.undistort(m, K, dist) for m in raw])
+    v = golden("box_views.npz")
+    with A.VoxelEngine(40, 40, 20, 0.007) as e:
+        e.set_views(v["P"][:2], 640, 480, v["M"][:2])
+        with pytest.raises(A.VoxCarveError):
+            e.set_masks_raw(raw)  # no calibration yet
+        e.set_calibration(K, dist)
+        e.set_masks_raw(raw)
+        assert np.array_equal(e.download_masks(), pack_bits((und == 0).all(-1)))
+        e.set_images_raw(img)
+        assert np.array_equal(e.download_images()[0], cv2.imdecode(z["box_image0003_dst"], 1))
+        e.carve()
+        occ = e.download_occupied()
+    ro, _ = oracle.carve(40, 40, 20, np.float32(0.007), v["P"][:2], 640, 480, mask_bgr=und)
+    assert np.array_equal(occ, ro)

@@ -192,3 +192,15 @@ def test_closure_rejects_even_kernel_and_dilates(oracle):
     assert (out[:, 3] > 0).sum() == 4 * 3 * 3            # x in 0..3, all y in 0..2 (y = 3 is 2 away), all z
     assert np.array_equal(out[0 + 5 * (0 + 4 * 0)], (10, 20, 30, 1))          # only the first voxel in reach
     assert np.array_equal(out[1 + 5 * (0 + 4 * 0)], (30, 40, 50, 1))          # mean of both
+
+
+def test_undistort_matches_cv2_kat(oracle, golden):
+    """cv::undistort (VoxelCarving.cpp:36): the oracle restatement against cv2 4.13.0 outputs, byte for byte — dataset images
+    and masks, a strongly distorted random image, the 8-coefficient rational model with a skewed K, a tall 33-px-wide image."""
+    import cv2  # PNG decode of the fixture only
+    z = golden("undistort_kat.npz")
+    for n in z["names"]:
+        src, dst = cv2.imdecode(z[f"{n}_src"], 1), cv2.imdecode(z[f"{n}_dst"], 1)
+        assert np.array_equal(oracle.undistort(src, z[f"{n}_K"], z[f"{n}_dist"]), dst), n
+    with pytest.raises(ValueError):
+        oracle.undistort(src, z[f"{n}_K"], [0.1, 0.2, 0.3])

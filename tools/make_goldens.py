@@ -265,6 +265,30 @@ def soft_golden():
     print(f"  soft_box_1off.json: {nv} vertices / {nf} faces")
 
 
+def undistort_kat():
+    """cv2.undistort (VoxelCarving.cpp:36, ColorReconstruction.h:23) known answers: raw inputs + outputs, PNG-compressed."""
+    rng = np.random.default_rng(7)
+    K, dist = read_calibration(os.path.join(REF, "Data/box_dataset/cameracalibration.yml"))
+    cases = []
+    cases.append(("box_mask0000", cv2.imread(os.path.join(REF, "Data/box_dataset/masks/mask0000.jpg"), 1), K, dist))
+    cases.append(("box_image0003", cv2.imread(os.path.join(REF, "Data/box_dataset/images/image0003.jpg"), 1), K, dist))
+    cases.append(("human_mask_5", cv2.imread(os.path.join(REF, "Data/human_dataset/masks/5.jpg"), 1), K, dist))
+    K2 = np.array([[150.3, 0, 99.7], [0, 149.1, 60.2], [0, 0, 1]])
+    cases.append(("random_strong5", rng.integers(0, 256, (123, 201, 3), dtype=np.uint8), K2, np.array([[0.4, -0.9, 0.01, -0.02, 0.3]])))
+    cases.append(("random_k8", rng.integers(0, 256, (97, 130, 3), dtype=np.uint8), np.array([[90.5, 0.3, 64.2], [0, 91.5, 48.9], [0, 0, 1]]),
+                  np.array([[0.2, -0.1, 0.003, 0.004, 0.05, 0.1, -0.05, 0.02]])))
+    cases.append(("random_4coef_tall", rng.integers(0, 256, (301, 33, 3), dtype=np.uint8), np.array([[40.0, 0, 16.0], [0, 42.0, 150.0], [0, 0, 1]]),
+                  np.array([[-0.3, 0.1, 0.0, 0.0]])))
+    out = {}
+    for name, img, Kc, dc in cases:
+        ref = cv2.undistort(img, Kc, dc)
+        ok1, a = cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        ok2, b = cv2.imencode(".png", ref, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        out[name + "_src"], out[name + "_dst"], out[name + "_K"], out[name + "_dist"] = a.ravel(), b.ravel(), Kc, dc
+    np.savez_compressed(os.path.join(OUT, "undistort_kat.npz"), names=np.array([c[0] for c in cases]), **out)
+    print(f"  undistort_kat.npz: {len(cases)} cases (cv2 {cv2.__version__})")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     print("cv2", cv2.__version__)
@@ -274,6 +298,7 @@ def main():
     literal_run(box, 24, 20, 12, 0.012, "box_literal.npz")
     literal_run(human, 20, 24, 28, 0.011, "human_literal.npz")
     soft_golden()
+    undistort_kat()
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         print(f"  {f:24s} {os.path.getsize(p):9d} B sha256={hashlib.sha256(open(p,'rb').read()).hexdigest()[:16]}")
