@@ -27,7 +27,9 @@ unsigned long long g_next_uid = 1;
 
 }  // namespace
 
+extern "C" {
 static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream);
+}
 
 struct vc_engine {
     vc_grid_desc g{};
