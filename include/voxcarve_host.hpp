@@ -43,6 +43,11 @@ struct ViewCache {
     std::vector<uint32_t> mask_bits;  // V*H*ceil(W/32), 1 = background; or ...
     std::vector<uint8_t> mask_bgr;    // ... V*H*W*3 undistorted 8UC3 masks (VoxelCarving.cpp:36)
     std::vector<uint8_t> images_bgr;  // V*H*W*3 undistorted images (ColorReconstruction.h:23); empty if no colouring
+    // raw = true: mask_bgr / images_bgr are the DISTORTED 8UC3 inputs as cv::imread delivers them, and the engine runs
+    // cv::undistort on the device (bit-exact with OpenCV's 8UC3 path) using K / dist from cameracalibration.yml
+    bool raw = false;
+    double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> dist;         // k1 k2 p1 p2 [k3 [k4 k5 k6]]
 };
 
 struct McSummary {
@@ -65,11 +70,12 @@ class Engine {
     void setViews(const ViewCache& c, bool with_images) {
         if ((int)c.P.size() != c.V * 12) throw Error(VC_ERR_ARG, "ViewCache.P must hold V*12 floats");
         check(vc_set_views(h_, c.V, c.W, c.H, c.P.data(), c.M.empty() ? nullptr : c.M.data()));
+        if (c.raw) check(vc_set_calibration(h_, c.K, c.dist.data(), (int32_t)c.dist.size()));
         if (!c.mask_bits.empty()) check(vc_set_masks(h_, c.mask_bits.data(), VC_MASK_BITS));
-        else if (!c.mask_bgr.empty()) check(vc_set_masks(h_, c.mask_bgr.data(), VC_MASK_BGR8));
+        else if (!c.mask_bgr.empty()) check(vc_set_masks(h_, c.mask_bgr.data(), c.raw ? VC_MASK_BGR8_RAW : VC_MASK_BGR8));
         if (with_images) {
             if (c.images_bgr.empty()) throw Error(VC_ERR_ARG, "colour reconstruction needs ViewCache.images_bgr");
-            check(vc_set_images(h_, c.images_bgr.data()));
+            check(c.raw ? vc_set_images_raw(h_, c.images_bgr.data()) : vc_set_images(h_, c.images_bgr.data()));
         }
         check(vc_synchronize(h_));  // the cache may be a temporary
     }

@@ -31,8 +31,9 @@
 namespace vc {
 
 // Everything the reference recomputes per call, computed once: pose per image
-// (estimatePoseFromImage + inv, VoxelCarving.cpp:25-26), P = intr(CV_32F) * pose(3x4) (:19,29-30,41),
-// undistorted masks / images (:36, ColorReconstruction.h:23).  Keyed on the image data pointers so that
+// (estimatePoseFromImage + inv, VoxelCarving.cpp:25-26), P = intr(CV_32F) * pose(3x4) (:19,29-30,41).
+// Masks / images are handed over RAW: the engine runs cv::undistort (:36, ColorReconstruction.h:23) on the device,
+// bit-exact with OpenCV's 8UC3 path.  Keyed on the image data pointers so that
 // carve() followed by reconstruct*Color() on the same vectors (main.cpp:260-288) estimates poses once.
 inline const ViewCache& cachedViews(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, std::vector<cv::Mat>& images,
                                     std::vector<cv::Mat>& masks, bool need_images) {
@@ -48,20 +49,22 @@ inline const ViewCache& cachedViews(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, 
     cache.H = images[0].rows;
     cv::Mat intr = cameraMatrix.clone();
     intr.convertTo(intr, CV_32F);
+    cv::Mat K64, D64;
+    cameraMatrix.convertTo(K64, CV_64F);
+    distCoeffs.convertTo(D64, CV_64F);
+    cache.raw = true;
+    for (int i = 0; i < 9; i++) cache.K[i] = K64.at<double>(i / 3, i % 3);
+    for (int i = 0; i < (int)D64.total(); i++) cache.dist.push_back(D64.at<double>(i));
     for (size_t i = 0; i < images.size(); i++) {
         cv::Mat pose = estimatePoseFromImage(cameraMatrix, distCoeffs, images[i], false).inv();
         cv::Mat M = pose(cv::Rect(0, 0, 4, 3)).clone();
         cv::Mat P = intr * M;  // cv::gemm, 3x3 . 3x4 CV_32F — the loop-invariant half of VoxelCarving.cpp:19
         cache.M.insert(cache.M.end(), (float*)M.data, (float*)M.data + 12);
         cache.P.insert(cache.P.end(), (float*)P.data, (float*)P.data + 12);
-        cv::Mat um;
-        cv::undistort(masks[i], um, cameraMatrix, distCoeffs);
-        um = um.isContinuous() ? um : um.clone();
+        const cv::Mat um = masks[i].isContinuous() ? masks[i] : masks[i].clone();
         cache.mask_bgr.insert(cache.mask_bgr.end(), um.data, um.data + (size_t)um.rows * um.cols * 3);
         if (need_images) {
-            cv::Mat ui;
-            cv::undistort(images[i], ui, cameraMatrix, distCoeffs);
-            ui = ui.isContinuous() ? ui : ui.clone();
+            const cv::Mat ui = images[i].isContinuous() ? images[i] : images[i].clone();
             cache.images_bgr.insert(cache.images_bgr.end(), ui.data, ui.data + (size_t)ui.rows * ui.cols * 3);
         }
     }
