@@ -100,7 +100,6 @@ def cpu_reference(w, seconds, steps, warmup):
     """oracle.carve on a contiguous z-slab of the same workload, all host threads. -> (vv/s, cores, sample text, ms/step)"""
     from oracle import oracle as O
     nthr = O.max_threads()
-    bgr_ok = w.V * w.H * w.W * 3 < 1 << 31
     z_mid = w.Z // 2
 
     def run(n):
