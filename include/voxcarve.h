@@ -69,7 +69,7 @@ enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1, VC_MASK_BGR8_RAW = 2 /
 
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
-    double last_classify_ms;       /* of which: brick classification kernel (0 for the flat modes) */
+    double last_classify_ms;       /* of which: the two brick-classification kernels + the fill pass (0 for the flat modes) */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
     uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
