@@ -70,7 +70,7 @@ struct vc_engine {
     unsigned long long *d_block_sums = nullptr, *d_scalars = nullptr;  // scalars: [0]=total surf, [1]=n_list(u32), [2]=executed, [3..4]=popcounts
     unsigned long long* d_color_idx = nullptr;
     uchar4* d_color_rgbn = nullptr;
-    unsigned long long n_surface = 0;
+    unsigned long long n_surface = 0, color_capacity = 0;  // colour record buffers are grow-only
     bool have_colors = false;
     unsigned long long* d_hist = nullptr;
     bool have_mc = false;
@@ -184,6 +184,7 @@ int launch_carve(vc_engine* e, int mode, const VcCarveParams& p, bool count) {
 void free_color(vc_engine* e) {
     cudaFree(e->d_color_idx); e->d_color_idx = nullptr;
     cudaFree(e->d_color_rgbn); e->d_color_rgbn = nullptr;
+    e->color_capacity = 0;
     e->have_colors = false;
     e->n_surface = 0;
 }
@@ -932,7 +933,8 @@ int vc_color(vc_engine* e, int32_t color_mode) {
         VC_CUDA(e, cudaMalloc(&e->d_list, n * 4));
         VC_CUDA(e, cudaMalloc(&e->d_block_sums, (size_t)nb * sizeof(unsigned long long)));
     }
-    free_color(e);
+    e->have_colors = false;
+    e->n_surface = 0;
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars, 0, 2 * sizeof(unsigned long long), e->stream));
     const VcVolView g = vol_view(e);
     vc_surface_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(g, e->g.z_begin, e->nz, e->d_surf, e->d_counts, e->d_list,
@@ -950,8 +952,13 @@ int vc_color(vc_engine* e, int32_t color_mode) {
     if (total > 0xffffffffull) return fail(e, VC_ERR_CAPACITY, "vc_color: %llu surface voxels exceed 32-bit offsets", total);
     e->n_surface = total;
     if (total) {
-        VC_CUDA(e, cudaMalloc(&e->d_color_idx, total * sizeof(unsigned long long)));
-        VC_CUDA(e, cudaMalloc(&e->d_color_rgbn, total * sizeof(uchar4)));
+        if (total > e->color_capacity) {
+            free_color(e);
+            e->n_surface = total;
+            VC_CUDA(e, cudaMalloc(&e->d_color_idx, total * sizeof(unsigned long long)));
+            VC_CUDA(e, cudaMalloc(&e->d_color_rgbn, total * sizeof(uchar4)));
+            e->color_capacity = total;
+        }
         VcColorParams p{};
         p.surf = e->d_surf; p.offsets = e->d_counts; p.list = e->d_list; p.images = e->d_images;
         p.idx_out = e->d_color_idx; p.rgbn_out = e->d_color_rgbn; p.n_list = n_list;
@@ -959,7 +966,10 @@ int vc_color(vc_engine* e, int32_t color_mode) {
         p.W = e->W; p.H = e->H; p.V = e->V;
         p.Wm05 = (float)e->W - 0.5f; p.Hm05 = (float)e->H - 0.5f; p.s = e->g.voxel_size;
         p.mode = color_mode;
-        vc_surface_color_kernel<<<(n_list + 3) / 4, 128, 0, e->stream>>>(p);
+        p.n_surface = total;
+        vc_surface_expand_kernel<<<(n_list + 3) / 4, 128, 0, e->stream>>>(p);
+        if (color_mode == VC_COLOR_CLOSEST) vc_surface_color_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
+        else vc_surface_color_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
         VC_CUDA(e, cudaGetLastError());
     }
     e->have_colors = true;
@@ -999,8 +1009,10 @@ int vc_mc_classify(vc_engine* e) {
     const int Cw = (e->g.X + 1 + 31) / 32;
     const long long n = (long long)n_cz * (e->g.Y + 1) * Cw;
     VC_CUDA(e, cudaMemsetAsync(e->d_hist, 0, 256 * sizeof(unsigned long long), e->stream));
-    long long blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    const long long n_tasks = (long long)n_cz * ((e->g.Y + 1 + VC_MC_ROWS - 1) / VC_MC_ROWS) * ((Cw + 31) / 32);  // one warp each
+    long long blocks = (n_tasks + 7) / 8;
+    if (blocks > (long long)e->sm_count * 16) blocks = (long long)e->sm_count * 16;
+    (void)n;
     vc_mc_classify_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(vol_view(e), cz_begin, n_cz, Cw, e->d_hist);
     VC_CUDA(e, cudaGetLastError());
     e->have_mc = true;
