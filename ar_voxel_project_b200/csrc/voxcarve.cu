@@ -781,50 +781,47 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     if (bind_device(e)) return VC_ERR_CUDA;
     int rc = ensure_constants(e);
     if (rc) return rc;
-    const int LZ = VC_BZ * VC_SUPER;  // planes per super-brick layer
+    for (int k = 0; k <= n_parts; k++) z_bounds[k] = e->g.z_begin + (int)((long long)k * e->nz / n_parts);  // uniform fallback
     const int nbx = e->Wx, nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+    if (nbz < n_parts) return VC_OK;  // fewer brick layers than parts: keep the uniform split
+    rc = ensure_brick_buffers(e);
+    if (rc) return rc;
+    // both classification levels of VC_EXACT over the whole range, no volumes touched
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
     const long long n_super = (long long)sbx * sby * sbz;
-    for (int k = 0; k <= n_parts; k++) z_bounds[k] = e->g.z_begin + (int)((long long)k * e->nz / n_parts);  // uniform fallback
-    if (sbz < n_parts) return VC_OK;  // fewer layers than parts: keep the uniform split
-    VcBrickState* d_states = nullptr;
-    uint8_t* d_flags = nullptr;
-    unsigned int* d_list = nullptr;
-    VC_CUDA(e, cudaMalloc(&d_states, (size_t)n_super * sizeof(VcBrickState)));
-    VC_CUDA(e, cudaMalloc(&d_flags, (size_t)n_super));
-    VC_CUDA(e, cudaMalloc(&d_list, ((size_t)n_super + 1) * sizeof(unsigned int)));
-    VC_CUDA(e, cudaMemsetAsync(d_list + n_super, 0, sizeof(unsigned int), e->stream));
-    VcBrickParams sp{};
-    sp.dense = d_states; sp.super_flags = d_flags; sp.super_list = d_list; sp.n_super_list = d_list + n_super; sp.sat = e->d_sat;
-    sp.X = e->g.X; sp.Y = e->g.Y; sp.Wx = e->Wx; sp.nz = e->nz; sp.z_begin = e->g.z_begin;
-    sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz; sp.W = e->W; sp.H = e->H; sp.v0 = 0; sp.v1 = e->V; sp.s = e->g.voxel_size;
+    unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);
+    VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
+    VcBrickParams bp{};
+    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
+    bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
+    bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
+    bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = 0; bp.v1 = e->V; bp.s = e->g.voxel_size;
+    VcBrickParams sp = bp;
+    sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
     vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
-    std::vector<VcBrickState> h((size_t)n_super);
-    cudaError_t s = cudaMemcpyAsync(h.data(), d_states, (size_t)n_super * sizeof(VcBrickState), cudaMemcpyDeviceToHost, e->stream);
-    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
-    cudaFree(d_states); cudaFree(d_flags); cudaFree(d_list);
-    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_plan_slabs: %s", cudaGetErrorString(s));
-    // cost of a layer: undecided views of its undecided super-bricks (per-voxel + brick-level work) plus a small
-    // constant per super-brick (fill pass)
-    std::vector<double> cost((size_t)sbz, 0.0);
+    bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
+    vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);
+    unsigned int counts[2] = {0, 0};
+    VC_CUDA(e, cudaMemcpyAsync(counts, d_nlist, sizeof counts, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<VcBrickState> h((size_t)counts[0]);
+    if (counts[0]) VC_CUDA(e, cudaMemcpy(h.data(), e->d_bricks, (size_t)counts[0] * sizeof(VcBrickState), cudaMemcpyDeviceToHost));
+    // cost of a brick layer (8 planes): per-voxel work of its listed bricks (undecided views x voxels) plus a small constant
+    // per plane for the classification and fill passes
+    std::vector<double> cost((size_t)nbz, 0.0);
     double total = 0.0;
-    for (int z = 0; z < sbz; z++) {
-        double c = 0.0;
-        for (long long i = 0; i < (long long)sbx * sby; i++) {
-            const VcBrickState& st = h[(size_t)z * sbx * sby + i];
-            c += 0.05;
-            if (!(st.flags & VC_BRICK_CARVED)) c += (double)st.n_und;
-        }
-        cost[z] = c;
-        total += c;
-    }
+    for (const VcBrickState& st : h) cost[st.brick / ((unsigned)nbx * (unsigned)nby)] += (double)st.n_und * (VC_BX * VC_BY * VC_BZ);
+    for (int z = 0; z < nbz; z++) total += cost[z];
+    const double floor_cost = total > 0 ? 0.03 * total / nbz : 1.0;
+    total = 0.0;
+    for (int z = 0; z < nbz; z++) { cost[z] += floor_cost; total += cost[z]; }
     int layer = 0;
     double acc = 0.0;
     for (int k = 1; k < n_parts; k++) {
         const double target = total * k / n_parts;
-        while (layer < sbz - (n_parts - k) && acc + cost[layer] * 0.5 < target) acc += cost[layer++];
+        while (layer < nbz - (n_parts - k) && acc + cost[layer] * 0.5 < target) acc += cost[layer++];
         if (layer < k) { acc += cost[layer]; layer = k; }  // every part gets at least one layer
-        z_bounds[k] = e->g.z_begin + layer * LZ;
+        z_bounds[k] = e->g.z_begin + layer * VC_BZ;
     }
     return VC_OK;
 }

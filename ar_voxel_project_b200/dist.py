@@ -29,7 +29,12 @@ def all_gather_slabs(full, Z, world=None, group=None, bounds=None):
     sizes = {bounds[r + 1] - bounds[r] for r in range(world)}
     if len(sizes) == 1:
         dist.all_gather_into_tensor(flat.view(-1), flat[bounds[rank]:bounds[rank + 1]].reshape(-1), group=group)
-    else:  # ragged slabs: one broadcast per owner
+    elif dist.get_backend(group) == "nccl":
+        # ragged slabs: torch's NCCL all_gather takes per-rank output views of different sizes and issues the per-owner
+        # broadcasts inside one ncclGroup (one launch, all links busy at once)
+        outs = [flat[bounds[r]:bounds[r + 1]] for r in range(world)]
+        dist.all_gather(outs, flat[bounds[rank]:bounds[rank + 1]], group=group)
+    else:  # gloo (CPU tests): one broadcast per owner
         for r in range(world):
             a, b = bounds[r], bounds[r + 1]
             if b > a:

@@ -137,9 +137,10 @@ VC_EXPORT int vc_color(vc_engine* e, int32_t color_mode);
 VC_EXPORT int vc_mc_classify(vc_engine* e);
 
 /* ---- multi-GPU plumbing ---------------------------------------------------------- */
-/* Balanced contiguous z-slabs for n_parts GPUs.  Runs only the super-brick classification of VC_EXACT over this engine's
- * z-range (needs views + masks, allocates no volumes), estimates the work per layer of 32 planes and returns n_parts+1
- * boundaries (interior ones multiples of 32 planes from z_begin) with z_bounds[0] = z_begin, z_bounds[n_parts] = z_end.
+/* Balanced contiguous z-slabs for n_parts GPUs.  Runs only the two brick-classification passes of VC_EXACT over this
+ * engine's z-range (needs views + masks, allocates no volumes), takes the per-voxel work left per layer of 8 planes
+ * (undecided views x voxels of the listed bricks) and returns n_parts+1 boundaries (interior ones multiples of 8 planes
+ * from z_begin) with z_bounds[0] = z_begin, z_bounds[n_parts] = z_end.
  * Deterministic: every rank computes the same split from the same inputs. */
 VC_EXPORT int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds);
 /* Re-range an engine to the slab [z_begin, z_end) of the same grid, keeping views, masks and SAT (plan on the whole grid,

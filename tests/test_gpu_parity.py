@@ -363,7 +363,7 @@ def test_fast_carve_matches_oracle_bfs(A, oracle, golden, case):
 
 
 def test_planned_slabs_tile_the_grid_and_match(A, oracle):
-    """vc_plan_slabs / vc_set_slab: balanced contiguous slabs (boundaries on 32-plane layers) carve to the same bits"""
+    """vc_plan_slabs / vc_set_slab: balanced contiguous slabs (boundaries on 8-plane brick layers) carve to the same bits"""
     from ar_voxel_project_b200.synth import Workload
     X, Y, Z = 96, 64, 160
     w = Workload(160, 8, 320, 240, seed=6, dims=(X, Y, Z))
@@ -374,7 +374,7 @@ def test_planned_slabs_tile_the_grid_and_match(A, oracle):
         full = e.download_occupied(), e.download_seen()
         for n in (1, 2, 3, 5):
             b = e.plan_slabs(n)
-            assert b[0] == 0 and b[-1] == Z and all(x < y for x, y in zip(b[:-1], b[1:])) and all(x % 32 == 0 for x in b[:-1])
+            assert b[0] == 0 and b[-1] == Z and all(x < y for x, y in zip(b[:-1], b[1:])) and all(x % 8 == 0 for x in b[:-1])
         with pytest.raises(A.VoxCarveError):
             e.plan_slabs(Z + 1)
         b = e.plan_slabs(3)
