@@ -535,3 +535,65 @@ def test_device_undistort_matches_cv2_kat_and_raw_mask_path(A, oracle, golden):
         occ = e.download_occupied()
     ro, _ = oracle.carve(40, 40, 20, np.float32(0.007), v["P"][:2], 640, 480, mask_bgr=und)
     assert np.array_equal(occ, ro)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_hierarchical_carve_random_stress(A, oracle, seed):
+    """random grids / slabs / view counts / image sizes / camera placements (incl. cameras inside or grazing the grid, so that
+    depth changes sign inside bricks and whole bricks fall outside the image): VC_EXACT == VC_EXACT_FLAT == oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    X, Y, Z = (int(rng.integers(1, 140)), int(rng.integers(1, 75)), int(rng.integers(1, 75)))
+    V = int(rng.choice([1, 2, 7, 31, 32, 33, 40, 65, 70]))
+    W, H = int(rng.integers(8, 300)), int(rng.integers(8, 200))
+    s = np.float32(rng.uniform(0.002, 0.02))
+    ext = np.array([Y * s, X * s, Z * s])  # world extents: (y*s, x*s, -z*s)
+    centre = np.array([ext[0] / 2, ext[1] / 2, -ext[2] / 2])
+    P = []
+    for v in range(V):
+        kind = rng.integers(0, 4)
+        if kind == 0:    # outside, looking at the grid
+            pos = centre + rng.normal(size=3) * ext.max() * rng.uniform(1.0, 3.0)
+        elif kind == 1:  # inside the grid
+            pos = centre + (rng.random(3) - 0.5) * ext * 0.8
+        elif kind == 2:  # on a face
+            pos = centre + (rng.random(3) - 0.5) * ext
+            pos[rng.integers(0, 3)] = centre[0] + ext[0] / 2
+        else:            # far away, narrow view: most bricks outside the image
+            pos = centre + rng.normal(size=3) * ext.max() * 6
+        target = centre + (rng.random(3) - 0.5) * ext * (0.2 if kind != 3 else 3.0)
+        zc = target - pos
+        zc /= np.linalg.norm(zc) + 1e-12
+        up = rng.normal(size=3)
+        xc = np.cross(zc, up)
+        xc /= np.linalg.norm(xc) + 1e-12
+        yc = np.cross(zc, xc)
+        R = np.stack([xc, yc, zc])
+        f = W * rng.uniform(0.4, 2.5)
+        K = np.array([[f, 0, W / 2 + rng.normal() * 3], [0, f * rng.uniform(0.9, 1.1), H / 2 + rng.normal() * 3], [0, 0, 1]])
+        M = np.concatenate([R, (-R @ pos)[:, None]], axis=1).astype(np.float32)
+        P.append(oracle.gemm3x3_3x4(K.astype(np.float32), M))
+    P = np.stack(P)
+    # blobby random masks: large background / foreground regions plus noise, so that whole bricks are decided
+    yy, xx = np.mgrid[0:H, 0:W]
+    bg = np.zeros((V, H, W), bool)
+    for v in range(V):
+        cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(0.1, 0.8) * max(W, H)
+        bg[v] = ((xx - cx) ** 2 + (yy - cy) ** 2) > r * r
+        bg[v] ^= rng.random((H, W)) < rng.choice([0.0, 0.0, 0.02])
+    from ar_voxel_project_b200.synth import pack_bits
+    bits = pack_bits(bg)
+    z0 = int(rng.integers(0, Z))
+    z1 = int(rng.integers(z0 + 1, Z + 1))
+    ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits, z0=z0, z1=z1)
+    occ, seen, _ = _carve(A, X, Y, Z, s, P, W, H, bits=bits, z0=z0, z1=z1)   # runs VC_EXACT and VC_EXACT_FLAT
+    assert np.array_equal(occ, ro), f"occupied differs (X,Y,Z,V,W,H,z0,z1)={(X, Y, Z, V, W, H, z0, z1)}"
+    assert np.array_equal(seen, rs), f"seen differs (X,Y,Z,V,W,H,z0,z1)={(X, Y, Z, V, W, H, z0, z1)}"
+    # and in two view ranges that split a 32-view word
+    if V > 2:
+        with A.VoxelEngine(X, Y, Z, s, z_begin=z0, z_end=z1) as e:
+            e.set_views(P, W, H)
+            e.set_masks_bits(bits)
+            cut = int(rng.integers(1, V))
+            e.carve(0, 0, cut)
+            e.carve(0, cut, -1)
+            assert np.array_equal(e.download_occupied(), ro) and np.array_equal(e.download_seen(), rs)
