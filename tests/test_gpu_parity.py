@@ -537,7 +537,7 @@ def test_device_undistort_matches_cv2_kat_and_raw_mask_path(A, oracle, golden):
     assert np.array_equal(occ, ro)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("VC_STRESS_SEEDS", "10"))))
 def test_hierarchical_carve_random_stress(A, oracle, seed):
     """random grids / slabs / view counts / image sizes / camera placements (incl. cameras inside or grazing the grid, so that
     depth changes sign inside bricks and whole bricks fall outside the image): VC_EXACT == VC_EXACT_FLAT == oracle"""
