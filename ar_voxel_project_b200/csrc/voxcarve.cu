@@ -559,7 +559,6 @@ static VcCarveParams carve_params(vc_engine* e, int view_begin, int view_end) {
     p.YB = (e->g.Y + VC_TILE_ROWS - 1) / VC_TILE_ROWS;
     p.z_begin = e->g.z_begin; p.nz = e->nz;
     p.W = e->W; p.H = e->H; p.Ww = e->Ww;
-    p.Wm05 = (float)e->W - 0.5f; p.Hm05 = (float)e->H - 0.5f;
     p.mask_plane = (uint32_t)((size_t)e->H * e->Ww);
     p.v0 = view_begin; p.v1 = view_end;
     p.s = e->g.voxel_size;
@@ -961,7 +960,7 @@ int vc_color(vc_engine* e, int32_t color_mode) {
         p.idx_out = e->d_color_idx; p.rgbn_out = e->d_color_rgbn; p.n_list = n_list;
         p.X = e->g.X; p.Y = e->g.Y; p.Wx = e->Wx; p.z_begin = e->g.z_begin;
         p.W = e->W; p.H = e->H; p.V = e->V;
-        p.Wm05 = (float)e->W - 0.5f; p.Hm05 = (float)e->H - 0.5f; p.s = e->g.voxel_size;
+        p.s = e->g.voxel_size;
         p.mode = color_mode;
         p.n_surface = total;
         vc_surface_expand_kernel<<<(n_list + 3) / 4, 128, 0, e->stream>>>(p);
