@@ -49,7 +49,9 @@ struct vc_engine {
     int V = 0, W = 0, H = 0, Ww = 0;
     unsigned long long views_version = 0;
     std::vector<VcViewConst> h_view;
-    std::vector<float> h_cam, h_absP;
+    std::vector<float> h_cam;
+    std::vector<VcViewFilter> h_filt;
+    float hDu = 0.f, hDv = 0.f;          // thresholds of the per-voxel filter (vc_filter_constants)
     bool have_M = false;
     uint32_t* d_mask = nullptr;
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
@@ -121,7 +123,7 @@ int ensure_constants(vc_engine* e) {
     if (o.uid == e->uid && o.version == e->views_version) return VC_OK;
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_view, e->h_view.data(), sizeof(VcViewConst) * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_cam, e->h_cam.data(), sizeof(float) * 4 * e->V, 0, cudaMemcpyHostToDevice, e->stream));
-    VC_CUDA(e, cudaMemcpyToSymbolAsync(c_absP, e->h_absP.data(), sizeof(float) * 12 * e->V, 0, cudaMemcpyHostToDevice, e->stream));
+    VC_CUDA(e, cudaMemcpyToSymbolAsync(c_filt, e->h_filt.data(), sizeof(VcViewFilter) * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     // the host vectors may change right after this call returns; make the copy complete first
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     o.uid = e->uid;
@@ -189,6 +191,35 @@ void free_color(vc_engine* e) {
     e->n_surface = 0;
 }
 
+// Error-radius coefficients of the per-voxel f32 filter (derivation above vc_filter_coord in vc_kernels.cuh), in f64 with
+// every factor rounded up.  T_i bounds sum_k |P_ik w_k| over the WHOLE grid (any slab of it), w = (y s, x s, -z s, 1) as f32
+// products.  A view whose matrix is not finite, or so large that the f32 evaluation could overflow, gets Cu = Cv = +inf:
+// its voxel-views are then never "decided" and all go through the exact path.
+void vc_filter_constants(vc_engine* e) {
+    const double up = 1.0 + ldexp(1.0, -22);  // f32 rounding of the coordinate products, with room to spare
+    const double s = (double)e->g.voxel_size;
+    const double ax = (double)(e->g.X - 1) * s * up, ay = (double)(e->g.Y - 1) * s * up, az = (double)(e->g.Z - 1) * s * up;
+    const double W3 = (double)e->W + 3.0, H3 = (double)e->H + 3.0;
+    for (int v = 0; v < e->V; v++) {
+        VcViewFilter& f = e->h_filt[v];
+        double eta[3];
+        bool ok = true;
+        for (int i = 0; i < 3; i++) {
+            const double T = fabs((double)f.P[i * 4 + 0]) * ay + fabs((double)f.P[i * 4 + 1]) * ax + fabs((double)f.P[i * 4 + 2]) * az + fabs((double)f.P[i * 4 + 3]);
+            ok = ok && std::isfinite(T) && T < ldexp(1.0, 60);
+            eta[i] = 4.0 * ldexp(1.0, -24) * T * (1.0 + ldexp(1.0, -19)) + ldexp(1.0, -100);
+        }
+        const double Cu = (eta[0] + W3 * eta[2]) * (1.0 + ldexp(1.0, -19)), Cv = (eta[1] + H3 * eta[2]) * (1.0 + ldexp(1.0, -19));
+        f.Cu = ok ? nextafterf((float)Cu, INFINITY) : INFINITY;
+        f.Cv = ok ? nextafterf((float)Cv, INFINITY) : INFINITY;
+        f.pad[0] = f.pad[1] = 0.0f;
+    }
+    const double Du = W3 * ldexp(1.0, -22) * (1.0 + ldexp(1.0, -10)) + ldexp(1.0, -20);
+    const double Dv = H3 * ldexp(1.0, -22) * (1.0 + ldexp(1.0, -10)) + ldexp(1.0, -20);
+    e->hDu = nextafterf((float)(0.5 - Du), -INFINITY);
+    e->hDv = nextafterf((float)(0.5 - Dv), -INFINITY);
+}
+
 }  // namespace
 
 extern "C" {
@@ -240,7 +271,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
     VC_CREATE_CUDA(cudaEventCreate(&e->ev1));
     VC_CREATE_CUDA(cudaEventCreate(&e->evm));
-    VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 8 * sizeof(unsigned long long)));
+    VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
 #undef VC_CREATE_CUDA
     *out = e;
@@ -307,10 +338,10 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     if (e->mask_bytes / 4 > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: %d views of %dx%d exceed 2^31 mask words", V, W, H);
     e->h_view.resize(V);
     e->h_cam.assign((size_t)V * 4, 0.0f);
-    e->h_absP.assign((size_t)V * 12, 0.0f);
+    e->h_filt.assign((size_t)V, VcViewFilter{});
     for (int v = 0; v < V; v++) {
         for (int k = 0; k < 12; k++) e->h_view[v].P[k] = (double)P[v * 12 + k];
-        for (int k = 0; k < 12; k++) e->h_absP[v * 12 + k] = P[v * 12 + k] < 0 ? -P[v * 12 + k] : P[v * 12 + k];  // NaN stays NaN -> undecided
+        for (int k = 0; k < 12; k++) e->h_filt[v].P[k] = P[v * 12 + k];
         if (M) {
             e->h_cam[v * 4 + 0] = M[v * 12 + 3];
             e->h_cam[v * 4 + 1] = M[v * 12 + 7];
@@ -319,6 +350,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
         }
     }
     e->have_M = M != nullptr;
+    vc_filter_constants(e);
     e->views_version++;
     return VC_OK;
 }
@@ -562,6 +594,7 @@ static VcCarveParams carve_params(vc_engine* e, int view_begin, int view_end) {
     p.mask_plane = (uint32_t)((size_t)e->H * e->Ww);
     p.v0 = view_begin; p.v1 = view_end;
     p.s = e->g.voxel_size;
+    p.hDu = e->hDu; p.hDv = e->hDv;
     return p;
 }
 
@@ -593,9 +626,11 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
         p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0);
     if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
-    const unsigned pgrid = (unsigned)e->sm_count * 4u;  // persistent: 4 blocks of 8 warps per SM
-    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
-    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby);
+    int resident = 0;  // persistent grid: as many blocks of 8 warps as are resident at once
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, vc_carve_bricks<false>, 256, 0) != cudaSuccess || resident < 1) { cudaGetLastError(); resident = 2; }
+    const unsigned pgrid = (unsigned)e->sm_count * (unsigned)resident;
+    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat);
+    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat);
     VC_CUDA(e, cudaGetLastError());
     e->stats.carve_launches += 4;
     if (n_bricks_out) *n_bricks_out += (uint64_t)n_bricks;
@@ -621,6 +656,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     VcCarveParams p = carve_params(e, view_begin, view_end);
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 5, 0, sizeof(unsigned long long), e->stream));
+    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 8, 0, 3 * sizeof(unsigned long long), e->stream));
     if (mode == VC_EXACT) { rc = ensure_brick_buffers(e); if (rc) return rc; }
     if (mode != VC_EXACT) { rc = materialize_reset(e); if (rc) return rc; }
     set_mask_window(e, true);
@@ -641,9 +677,11 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)(view_end - view_begin);
     e->stats.executed_voxel_views = 0;
     e->stats.brick_corner_views = 0;
+    e->stats.filter_rows = e->stats.filter_slow_rows = e->stats.filter_mismatches = 0;
     e->stats.last_carve_ms = -1.0;  // resolved lazily in vc_get_stats
     if (count_executed) {
-        unsigned long long ex = 0, bc = 0, nl = 0;
+        unsigned long long ex = 0, bc = 0, nl = 0, fl[3] = {0, 0, 0};
+        VC_CUDA(e, cudaMemcpyAsync(fl, e->d_scalars + 8, sizeof fl, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&ex, e->d_scalars + 2, sizeof ex, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&bc, e->d_scalars + 5, sizeof bc, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&nl, e->d_scalars + 6, sizeof nl, cudaMemcpyDeviceToHost, e->stream));
@@ -651,6 +689,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         e->stats.bricks_listed = mode == VC_EXACT ? (nl & 0xffffffffull) : 0;
         e->stats.executed_voxel_views = ex + (mode == VC_EXACT ? bc : 0);
         e->stats.brick_corner_views = mode == VC_EXACT ? bc : 0;
+        if (mode == VC_EXACT) { e->stats.filter_rows = fl[0]; e->stats.filter_slow_rows = fl[1]; e->stats.filter_mismatches = fl[2]; }
     }
     e->gathered = false;
     e->have_colors = false;

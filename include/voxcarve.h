@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VC_API_VERSION 1
+#define VC_API_VERSION 2
 
 #if defined(__GNUC__)
 #define VC_EXPORT __attribute__((visibility("default")))
@@ -59,8 +59,9 @@ typedef struct vc_grid_desc {
  * accumulation of the 3x4.4x1 product rounded once to f32, IEEE f32 divides, round half away.
  * It is built from explicit intrinsics, so nvcc's -fmad setting cannot change it.  VC_EXACT classifies
  * 32x8x8-voxel bricks per view first (conservatively, against a summed-area table of the silhouette)
- * and evaluates only the undecided (brick, view) pairs per voxel; VC_EXACT_FLAT evaluates every
- * voxel-view until its run is empty.  Both produce the same bits.
+ * and evaluates only the undecided (brick, view) pairs per voxel, each voxel-view first through an f32 filter with a
+ * rigorous error radius and exactly (f64) only where the filter cannot tell the pixel; VC_EXACT_FLAT evaluates every
+ * voxel-view exactly until its run is empty.  Both produce the same bits.
  * VC_FAST_F32 is a diagnostic f32/FMA pipeline (not bit-exact; see tests/test_fast_mode.py). */
 enum vc_carve_mode { VC_EXACT = 0, VC_FAST_F32 = 1, VC_EXACT_FLAT = 2 };
 /* values of the reference's -color flag (main.cpp:30,278-288) */
@@ -78,6 +79,12 @@ typedef struct vc_stats {
     uint64_t flood_rounds;         /* sweep rounds of the last vc_fast_carve */
     uint64_t carve_launches;       /* kernel launches issued by this engine so far */
     uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
+    /* per-voxel f32 filter of VC_EXACT (counting runs only): 32-voxel rows evaluated, rows that needed the exact f64
+     * re-evaluation, and filter decisions that disagreed with the exact evaluation (every decision is cross-checked
+     * in a counting run; anything but 0 is a bug) */
+    uint64_t filter_rows;
+    uint64_t filter_slow_rows;
+    uint64_t filter_mismatches;
 } vc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------- */

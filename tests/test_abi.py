@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 def test_binding_covers_header_exactly(lib_built):
     from ar_voxel_project_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
-    assert _lib.load().vc_api_version() == 1
+    assert _lib.load().vc_api_version() == 2
 
 
 def test_no_torch_types_in_abi():

@@ -26,6 +26,9 @@ def _carve(A, X, Y, Z, s, P, W, H, bits=None, bgr=None, M=None, z0=0, z1=None, m
             e.set_masks_bgr(bgr)
         e.carve(mode, count_executed=count)
         out = e.download_occupied(), e.download_seen(), e.stats()
+        if mode == 0 and count:  # a counting run cross-checks every decision of the per-voxel f32 filter against the exact evaluation
+            assert out[2]["filter_mismatches"] == 0, f"f32 filter accepted {out[2]['filter_mismatches']} pixels the exact path rejects"
+            assert out[2]["filter_slow_rows"] <= out[2]["filter_rows"]
         if mode == 0:
             e.reset()
             e.carve(2)
@@ -63,7 +66,7 @@ def test_carve_ragged_grids_synthetic(A, oracle, dims):
     X, Y, Z = dims
     w = Workload(max(dims), 7, 320, 200, seed=5, dims=dims)
     ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
-    occ, seen, _ = _carve(A, X, Y, Z, w.s, w.P, w.W, w.H, bits=w.mask_bits)
+    occ, seen, _ = _carve(A, X, Y, Z, w.s, w.P, w.W, w.H, bits=w.mask_bits, count=True)
     assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
     if X % 32:
         assert (occ[..., -1] >> np.uint32(X % 32)).max() == 0 and (seen[..., -1] >> np.uint32(X % 32)).max() == 0
@@ -104,7 +107,7 @@ def test_carve_adversarial_cameras(A, oracle):
     bits = rng.integers(0, 2 ** 32, size=(len(P), H, (W + 31) // 32), dtype=np.uint64).astype(np.uint32)
     for v0 in range(len(P)):  # one view at a time, so a disagreement names its view
         ro, rs = oracle.carve(X, Y, Z, s, P[v0:v0 + 1], W, H, mask_bits=bits[v0:v0 + 1])
-        occ, seen, _ = _carve(A, X, Y, Z, s, P[v0:v0 + 1], W, H, bits=bits[v0:v0 + 1])
+        occ, seen, _ = _carve(A, X, Y, Z, s, P[v0:v0 + 1], W, H, bits=bits[v0:v0 + 1], count=True)
         assert np.array_equal(occ, ro), f"occupied differs for adversarial view {v0}"
         assert np.array_equal(seen, rs), f"seen differs for adversarial view {v0}"
     ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits)
@@ -500,6 +503,12 @@ def test_config4_1024cubed_full_size_properties(A, oracle):
         e.reset()
         e.carve(2)
         assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
+        e.reset()
+        e.carve(0, count_executed=True)  # every decision of the per-voxel f32 filter checked against the exact evaluation
+        st = e.stats()
+        assert st["filter_mismatches"] == 0 and st["filter_rows"] > 0
+        assert st["filter_slow_rows"] < 0.5 * st["filter_rows"], (st["filter_slow_rows"], st["filter_rows"])
+        assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
     assert ((~occ) & (~seen)).max() == 0
     assert 0.02 < n_occ / 1024 ** 3 < 0.25 and n_seen <= 1024 ** 3
     for z0 in (0, 511, 1022):
@@ -585,7 +594,7 @@ def test_hierarchical_carve_random_stress(A, oracle, seed):
     z0 = int(rng.integers(0, Z))
     z1 = int(rng.integers(z0 + 1, Z + 1))
     ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits, z0=z0, z1=z1)
-    occ, seen, _ = _carve(A, X, Y, Z, s, P, W, H, bits=bits, z0=z0, z1=z1)   # runs VC_EXACT and VC_EXACT_FLAT
+    occ, seen, _ = _carve(A, X, Y, Z, s, P, W, H, bits=bits, z0=z0, z1=z1, count=True)   # runs VC_EXACT (filter cross-checked) and VC_EXACT_FLAT
     assert np.array_equal(occ, ro), f"occupied differs (X,Y,Z,V,W,H,z0,z1)={(X, Y, Z, V, W, H, z0, z1)}"
     assert np.array_equal(seen, rs), f"seen differs (X,Y,Z,V,W,H,z0,z1)={(X, Y, Z, V, W, H, z0, z1)}"
     # and in two view ranges that split a 32-view word

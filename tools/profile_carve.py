@@ -21,8 +21,10 @@ with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
         e.reset()
         e.carve(a.mode)
         e.synchronize()
-        print("carve ms", e.stats()["last_carve_ms"])
+        st = e.stats()
+        print("carve ms", st["last_carve_ms"], "of which classify+fill", st["last_classify_ms"])
     e.reset()
     e.carve(a.mode, count_executed=True)
     st = e.stats()
     print("executed", st["executed_voxel_views"], "of which brick corners", st["brick_corner_views"], "nominal", st["nominal_voxel_views"], "occupied", e.count_occupied())
+    print("filter rows", st["filter_rows"], "slow rows", st["filter_slow_rows"], "mismatches", st["filter_mismatches"])
