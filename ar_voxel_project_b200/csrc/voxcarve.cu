@@ -39,6 +39,8 @@ struct vc_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished z-chunks while the next chunk is carving (vc_carve_download)
+    cudaStream_t fill_stream = nullptr;   // vc_fill*_kernel of a fresh VC_EXACT carve, next to vc_carve_bricks
+    cudaEvent_t ev_classified = nullptr, ev_filled = nullptr;
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_mid = false;
     // volumes
@@ -271,6 +273,9 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
     VC_CREATE_CUDA(cudaEventCreate(&e->ev1));
     VC_CREATE_CUDA(cudaEventCreate(&e->evm));
+    VC_CREATE_CUDA(cudaStreamCreateWithFlags(&e->fill_stream, cudaStreamNonBlocking));
+    VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_classified, cudaEventDisableTiming));
+    VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_filled, cudaEventDisableTiming));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
 #undef VC_CREATE_CUDA
@@ -293,6 +298,9 @@ void vc_destroy(vc_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evm) cudaEventDestroy(e->evm);
+    if (e->ev_classified) cudaEventDestroy(e->ev_classified);
+    if (e->ev_filled) cudaEventDestroy(e->ev_filled);
+    if (e->fill_stream) { cudaStreamSynchronize(e->fill_stream); cudaStreamDestroy(e->fill_stream); }
     for (int c = 0; c < 4; c++) if (e->ev_chunk[c]) cudaEventDestroy(e->ev_chunk[c]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -623,14 +631,38 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
     vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
-    vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
-        p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0);
+    // fresh carve: the fill pass skips the listed bricks and runs on its own stream next to the per-voxel kernel, which owns
+    // those bricks' words; otherwise it runs in order (it must apply the flags before the per-voxel kernel reads the state)
+    cudaStream_t fs = fresh ? e->fill_stream : e->stream;
+    if (fresh) {
+        VC_CUDA(e, cudaEventRecord(e->ev_classified, e->stream));
+        VC_CUDA(e, cudaStreamWaitEvent(fs, e->ev_classified, 0));
+    }
     if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
+    if (e->Wx % 4 == 0) {
+        const unsigned Q = (unsigned)e->Wx / 4u;
+        int q_shift = -1;
+        for (int b = 0; b < 31; b++) if (Q == (1u << b)) q_shift = b;
+        const unsigned per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
+        unsigned gy = (unsigned)p.nz;
+        if (fresh) {  // two small blocks per SM, looping over the planes: leaves most of every SM to vc_carve_bricks
+            gy = (2u * (unsigned)e->sm_count + per_plane - 1) / per_plane;
+            if (gy > (unsigned)p.nz) gy = (unsigned)p.nz;
+        }
+        vc_fill4_kernel<<<dim3(per_plane, gy), 256, 0, fs>>>(
+            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, fresh ? 1 : 0, q_shift, p.nz);
+    } else {
+        vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, fs>>>(
+            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, fresh ? 1 : 0);
+    }
+    if (fresh) VC_CUDA(e, cudaEventRecord(e->ev_filled, fs));
     int resident = 0;  // persistent grid: as many blocks of 8 warps as are resident at once
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, vc_carve_bricks<false>, 256, 0) != cudaSuccess || resident < 1) { cudaGetLastError(); resident = 2; }
+    if (fresh && resident > 2) resident--;  // room for the fill pass running next to it
     const unsigned pgrid = (unsigned)e->sm_count * (unsigned)resident;
-    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat);
-    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat);
+    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0);
+    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0);
+    if (fresh) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_filled, 0));  // the carve is complete on e->stream only with the fill
     VC_CUDA(e, cudaGetLastError());
     e->stats.carve_launches += 4;
     if (n_bricks_out) *n_bricks_out += (uint64_t)n_bricks;
