@@ -688,7 +688,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     VcCarveParams p = carve_params(e, view_begin, view_end);
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 2, 0, sizeof(unsigned long long), e->stream));
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 5, 0, sizeof(unsigned long long), e->stream));
-    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 8, 0, 3 * sizeof(unsigned long long), e->stream));
+    if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 8, 0, 4 * sizeof(unsigned long long), e->stream));
     if (mode == VC_EXACT) { rc = ensure_brick_buffers(e); if (rc) return rc; }
     if (mode != VC_EXACT) { rc = materialize_reset(e); if (rc) return rc; }
     set_mask_window(e, true);
@@ -709,10 +709,10 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)(view_end - view_begin);
     e->stats.executed_voxel_views = 0;
     e->stats.brick_corner_views = 0;
-    e->stats.filter_rows = e->stats.filter_slow_rows = e->stats.filter_mismatches = 0;
+    e->stats.filter_rows = e->stats.filter_slow_rows = e->stats.filter_mismatches = e->stats.subbrick_corner_views = 0;
     e->stats.last_carve_ms = -1.0;  // resolved lazily in vc_get_stats
     if (count_executed) {
-        unsigned long long ex = 0, bc = 0, nl = 0, fl[3] = {0, 0, 0};
+        unsigned long long ex = 0, bc = 0, nl = 0, fl[4] = {0, 0, 0, 0};
         VC_CUDA(e, cudaMemcpyAsync(fl, e->d_scalars + 8, sizeof fl, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&ex, e->d_scalars + 2, sizeof ex, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&bc, e->d_scalars + 5, sizeof bc, cudaMemcpyDeviceToHost, e->stream));
@@ -721,7 +721,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         e->stats.bricks_listed = mode == VC_EXACT ? (nl & 0xffffffffull) : 0;
         e->stats.executed_voxel_views = ex + (mode == VC_EXACT ? bc : 0);
         e->stats.brick_corner_views = mode == VC_EXACT ? bc : 0;
-        if (mode == VC_EXACT) { e->stats.filter_rows = fl[0]; e->stats.filter_slow_rows = fl[1]; e->stats.filter_mismatches = fl[2]; }
+        if (mode == VC_EXACT) { e->stats.filter_rows = fl[0]; e->stats.filter_slow_rows = fl[1]; e->stats.filter_mismatches = fl[2]; e->stats.subbrick_corner_views = fl[3]; }
     }
     e->gathered = false;
     e->have_colors = false;

@@ -9,9 +9,10 @@ BASELINE.json quotes the metric on (default C4: 1024^3 x 72 views, 1920x1080 sil
 `value`  = X*Y*Z*V (nominal voxel-view projections of the job) / device time, masks resident in HBM.
 `e2e`    = same metric through the C ABI with HOST buffers: per step H2D of P/M + the 8UC3 masks from pinned
            memory, reset, carve, D2H of both bit volumes into pinned memory; wall clock, max over ranks.
-`roofline` = per-voxel projections executed by the dominant kernel (vc_carve_bricks: what is left after the brick
-           classification and the __all_sync early exits) * 23 FLOP / that kernel's time against the measured FFMA
-           peak of this GPU (CUDA-core bound); `roofline_hbm` = grid-write bound of the whole carve.
+`roofline` = projections executed by the dominant kernel (vc_carve_bricks: the corner projections of its 8x8x8 sub-brick
+           classification + the per-voxel projections left after three levels of classification and the early exits)
+           * 23 FLOP / that kernel's time against the measured FFMA peak of this GPU (CUDA-core bound, SURVEY §8d);
+           `roofline_hbm` = grid-write bound of the whole carve against the copy bandwidth of MEASURED_PEAKS.json.
 `cpu_baseline` / --impl reference = oracle/ (C restatement of VoxelCarving.cpp:60-72) on a bounded z-slab sample.
 """
 import argparse
@@ -229,7 +230,7 @@ def run_ours(args):
     clk["sampled_over"] = f"{args.warmup} warm-up + {args.steps} timed + {n_tail} identical untimed steps"
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = allmax(float(np.mean(step_ms)))
-    launches = 4 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_fill_kernel (absorbs the reset), vc_carve_bricks per step
+    launches = 4 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_fill4_kernel (absorbs the reset) beside vc_carve_bricks, per step
 
     # carve-kernel-only time (events inside vc_carve) and executed voxel-views (separate, untimed counting pass)
     kt, ct = [], []
@@ -245,6 +246,8 @@ def run_ours(args):
     st = eng.stats()
     executed_total = allsum(float(st["executed_voxel_views"]))
     corner_total = allsum(float(st["brick_corner_views"]))
+    sub_corner_total = allsum(float(st["subbrick_corner_views"]))
+    filter_rows, filter_slow, filter_bad = (allsum(float(st[k])) for k in ("filter_rows", "filter_slow_rows", "filter_mismatches"))
     bricks_listed = allsum(float(st["bricks_listed"]))
     bricks_total = allsum(float(st["bricks_total"]))
     # the same job without brick classification (VC_EXACT_FLAT), for reference
@@ -350,7 +353,8 @@ def run_ours(args):
             pass
         kt_s = kernel_ms_max * 1e-3
         fine_s = fine_ms_max * 1e-3
-        exec_rank = (executed_total - corner_total) / world  # per-voxel projections of one vc_carve_bricks launch (rank average)
+        # projections of one vc_carve_bricks launch (rank average): per-voxel ones + the corners of its sub-brick classification
+        exec_rank = (executed_total - corner_total + sub_corner_total) / world
         ach = exec_rank * F_ALG / fine_s / 1e12
         alg_bytes = 2.0 * (Z / world) * Y * Wx * 4 + w.mask_bits.nbytes
         out = {
@@ -361,16 +365,22 @@ def run_ours(args):
             "executed_voxel_views": executed_total, "executed_fraction": executed_total / nominal_total,
             "executed_value": executed_total / (ms_per_step * 1e-3),
             "occupied_voxels": occupied_total, "carve_kernel_ms": kernel_ms_max,
-            "kernels_ms": {"vc_brick_classify_kernel": classify_ms_max, "vc_carve_bricks": fine_ms_max, "flat_vc_carve_rows_same_job": flat_ms},
-            "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total},
+            "kernels_ms": {"vc_brick_classify_kernel<1>+<0>": classify_ms_max, "vc_carve_bricks (vc_fill4_kernel beside it)": fine_ms_max,
+                           "flat_vc_carve_rows_same_job": flat_ms},
+            "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total,
+                       "of_which_sub_brick_level": sub_corner_total},
+            "filter": {"evaluations_x32": filter_rows, "exact_reevaluations_x32": filter_slow, "mismatches_vs_exact": filter_bad,
+                       "note": "per-voxel f32 filter with rigorous radius; every decision cross-checked against the exact path in the counting run"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma if ffma else None,
                          "traffic": traffic, "algorithmic_bytes": exec_rank / 8.0 + 2.0 * bricks_listed / world * 2048 / 8,
                          "kernel": "vc_carve_bricks",
-                         "how": f"per-voxel projections of one vc_carve_bricks launch ({exec_rank:.4g}) x {F_ALG:.0f} FLOP / its time "
-                                f"({fine_ms_max:.3f} ms); peak = FFMA microbenchmark on this GPU (vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s"},
+                         "how": f"projections of one vc_carve_bricks launch ({exec_rank:.4g}: per-voxel + sub-brick corners) x {F_ALG:.0f} FLOP / its time "
+                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve; the fill pass runs beside it); peak = FFMA microbenchmark on this GPU "
+                                f"(vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s. The kernel is issue-bound, see profiles/"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None,
-                             "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}"},
+                             "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": 2.0 * (Z / world) * Y * Wx * 4 / 3.68e12 * 1e3,
+                             "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}; "
+                                    "write_only_floor_ms = the two volumes at the 3.68 TB/s a cudaMemset reaches on this GPU (tools/memset_bench.py)"},
             "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris,
             "e2e": e2e, "e2e_bgr8": e2e_bgr, "gpu_launches": launches, "clocks": clk,
         }

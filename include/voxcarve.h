@@ -70,7 +70,8 @@ enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1, VC_MASK_BGR8_RAW = 2 /
 
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
-    double last_classify_ms;       /* of which: the two brick-classification kernels + the fill pass (0 for the flat modes) */
+    double last_classify_ms;       /* of which: the two brick-classification kernels (0 for the flat modes); the rest is the per-voxel
+                                      kernel with, on a fresh carve, the fill pass running beside it */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
     uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
@@ -82,9 +83,10 @@ typedef struct vc_stats {
     /* per-voxel f32 filter of VC_EXACT (counting runs only): 32-voxel rows evaluated, rows that needed the exact f64
      * re-evaluation, and filter decisions that disagreed with the exact evaluation (every decision is cross-checked
      * in a counting run; anything but 0 is a bug) */
-    uint64_t filter_rows;
+    uint64_t filter_rows;          /* in units of 32 voxel-views (one warp instruction stream) */
     uint64_t filter_slow_rows;
     uint64_t filter_mismatches;
+    uint64_t subbrick_corner_views; /* the part of brick_corner_views spent inside vc_carve_bricks (8x8x8 sub-brick level) */
 } vc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------- */
