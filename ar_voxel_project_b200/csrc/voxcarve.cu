@@ -628,9 +628,9 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = p.v0; bp.v1 = p.v1; bp.s = e->g.voxel_size;
     VcBrickParams sp = bp;  // level 1: super-bricks into the dense array
     sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
-    vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-    vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);  // blocks beyond the super-list exit at once
+    vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
     // fresh carve: the fill pass skips the listed bricks and runs on its own stream next to the per-voxel kernel, which owns
     // those bricks' words; otherwise it runs in order (it must apply the flags before the per-voxel kernel reads the state)
     cudaStream_t fs = fresh ? e->fill_stream : e->stream;
@@ -868,9 +868,9 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = 0; bp.v1 = e->V; bp.s = e->g.voxel_size;
     VcBrickParams sp = bp;
     sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
-    vc_brick_classify_kernel<1><<<(unsigned)((n_super * 8 + 255) / 256), 256, 0, e->stream>>>(sp);
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-    vc_brick_classify_kernel<0><<<(unsigned)(n_super * 2), 256, 0, e->stream>>>(bp);
+    vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
     unsigned int counts[2] = {0, 0};
     VC_CUDA(e, cudaMemcpyAsync(counts, d_nlist, sizeof counts, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
