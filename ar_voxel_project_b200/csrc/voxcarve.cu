@@ -56,6 +56,7 @@ struct vc_engine {
     float hDu = 0.f, hDv = 0.f;          // thresholds of the per-voxel filter (vc_filter_constants)
     bool have_M = false;
     uint32_t* d_mask = nullptr;
+    VcViewFilter* d_filt = nullptr;      // global copy of c_filt for lane-divergent reads (sub-brick classification)
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
     uint32_t* d_sat_tmp = nullptr;       // V x H x Ww word-column prefixes used while building d_sat
     uint8_t* d_bgr_tmp = nullptr;        // staging for 8UC3 masks (grow-only)
@@ -278,6 +279,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_filled, cudaEventDisableTiming));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
+    VC_CREATE_CUDA(cudaMalloc(&e->d_filt, VC_MAX_VIEWS * sizeof(VcViewFilter)));
 #undef VC_CREATE_CUDA
     *out = e;
     int rc = vc_reset(e);
@@ -292,7 +294,7 @@ void vc_destroy(vc_engine* e) {
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
     cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
-    cudaFree(e->d_scalars); cudaFree(e->d_hist);
+    cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -359,6 +361,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     }
     e->have_M = M != nullptr;
     vc_filter_constants(e);
+    VC_CUDA(e, cudaMemcpyAsync(e->d_filt, e->h_filt.data(), sizeof(VcViewFilter) * V, cudaMemcpyHostToDevice, e->stream));  // h_filt lives until the next vc_set_views, which synchronises first
     e->views_version++;
     return VC_OK;
 }
@@ -660,8 +663,8 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, vc_carve_bricks<false>, 256, 0) != cudaSuccess || resident < 1) { cudaGetLastError(); resident = 2; }
     if (fresh && resident > 2) resident--;  // room for the fill pass running next to it
     const unsigned pgrid = (unsigned)e->sm_count * (unsigned)resident;
-    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0);
-    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0);
+    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt);
+    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt);
     if (fresh) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_filled, 0));  // the carve is complete on e->stream only with the fill
     VC_CUDA(e, cudaGetLastError());
     e->stats.carve_launches += 4;
