@@ -71,7 +71,6 @@ struct vc_engine {
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
     // colour / mc results
-    uint32_t *d_surf = nullptr, *d_counts = nullptr, *d_list = nullptr;
     unsigned long long *d_block_sums = nullptr, *d_scalars = nullptr;  // scalars: [0]=total surf, [1]=n_list(u32), [2]=executed, [3..4]=popcounts
     unsigned long long* d_color_idx = nullptr;
     uchar4* d_color_rgbn = nullptr;
@@ -278,7 +277,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_classified, cudaEventDisableTiming));
     VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_filled, cudaEventDisableTiming));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
-    VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
+    VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 257 * sizeof(unsigned long long)));  // [256] = task counter of vc_mc_classify_kernel
     VC_CREATE_CUDA(cudaMalloc(&e->d_filt, VC_MAX_VIEWS * sizeof(VcViewFilter)));
 #undef VC_CREATE_CUDA
     *out = e;
@@ -293,7 +292,7 @@ void vc_destroy(vc_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
     cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
-    cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
+    cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
     free_color(e);
@@ -841,8 +840,8 @@ int vc_set_slab(vc_engine* e, int32_t z_begin, int32_t z_end) {
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); e->d_occ_own = e->d_seen_own = nullptr;
     cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     e->d_bricks = nullptr; e->d_super = nullptr; e->d_brick_flags = nullptr; e->d_super_flags = nullptr; e->d_super_list = nullptr;
-    cudaFree(e->d_surf); cudaFree(e->d_counts); cudaFree(e->d_list); cudaFree(e->d_block_sums);
-    e->d_surf = e->d_counts = e->d_list = nullptr; e->d_block_sums = nullptr;
+    cudaFree(e->d_block_sums);
+    e->d_block_sums = nullptr;
     free_color(e);
     return vc_reset(e);
 }
@@ -996,29 +995,20 @@ int vc_color(vc_engine* e, int32_t color_mode) {
     if (rc) return rc;
     const long long n = e->slab_words;
     if (n > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "vc_color: slab of %lld words too large", n);
-    const int nb = (int)((n + VC_SCAN_BLOCK - 1) / VC_SCAN_BLOCK);
-    if (!e->d_surf) {
-        VC_CUDA(e, cudaMalloc(&e->d_surf, n * 4));
-        VC_CUDA(e, cudaMalloc(&e->d_counts, n * 4));
-        VC_CUDA(e, cudaMalloc(&e->d_list, n * 4));
-        VC_CUDA(e, cudaMalloc(&e->d_block_sums, (size_t)nb * sizeof(unsigned long long)));
-    }
+    if (e->nz > 65535) return fail(e, VC_ERR_ARG, "vc_color: slab of %d planes too deep (grid dimension limit 65535)", e->nz);
+    const unsigned chunks = (unsigned)((e->plane_words + 1023) / 1024);  // blocks of vc_surface_pass_kernel per plane
+    const int nb = (int)(chunks * (unsigned)e->nz);
+    const dim3 sgrid(chunks, (unsigned)e->nz);
+    if (!e->d_block_sums) VC_CUDA(e, cudaMalloc(&e->d_block_sums, ((size_t)nb + 1) * sizeof(unsigned long long)));
     e->have_colors = false;
     e->n_surface = 0;
-    VC_CUDA(e, cudaMemsetAsync(e->d_scalars, 0, 2 * sizeof(unsigned long long), e->stream));
     const VcVolView g = vol_view(e);
-    vc_surface_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(g, e->g.z_begin, e->nz, e->d_surf, e->d_counts, e->d_list,
-                                                                          (unsigned int*)(e->d_scalars + 1));
+    vc_surface_pass_kernel<false><<<sgrid, 256, 0, e->stream>>>(g, e->g.z_begin, (unsigned)e->plane_words, e->d_block_sums, nullptr);
+    vc_scan_sums_kernel<<<1, 1024, 0, e->stream>>>(e->d_block_sums, nb, e->d_block_sums + nb);
     VC_CUDA(e, cudaGetLastError());
-    vc_scan_block_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(e->d_counts, e->d_counts, e->d_block_sums, n);
-    vc_scan_sums_kernel<<<1, 1024, 0, e->stream>>>(e->d_block_sums, nb, e->d_scalars);
-    vc_scan_add_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(e->d_counts, e->d_block_sums, n);
-    VC_CUDA(e, cudaGetLastError());
-    unsigned long long h[2];
-    VC_CUDA(e, cudaMemcpyAsync(h, e->d_scalars, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    unsigned long long total = 0;
+    VC_CUDA(e, cudaMemcpyAsync(&total, e->d_block_sums + nb, sizeof total, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
-    const unsigned long long total = h[0];
-    const unsigned int n_list = (unsigned int)h[1];
     if (total > 0xffffffffull) return fail(e, VC_ERR_CAPACITY, "vc_color: %llu surface voxels exceed 32-bit offsets", total);
     e->n_surface = total;
     if (total) {
@@ -1030,14 +1020,14 @@ int vc_color(vc_engine* e, int32_t color_mode) {
             e->color_capacity = total;
         }
         VcColorParams p{};
-        p.surf = e->d_surf; p.offsets = e->d_counts; p.list = e->d_list; p.images = e->d_images;
-        p.idx_out = e->d_color_idx; p.rgbn_out = e->d_color_rgbn; p.n_list = n_list;
+        p.images = e->d_images;
+        p.idx_out = e->d_color_idx; p.rgbn_out = e->d_color_rgbn;
         p.X = e->g.X; p.Y = e->g.Y; p.Wx = e->Wx; p.z_begin = e->g.z_begin;
         p.W = e->W; p.H = e->H; p.V = e->V;
         p.s = e->g.voxel_size;
         p.mode = color_mode;
         p.n_surface = total;
-        vc_surface_expand_kernel<<<(n_list + 3) / 4, 128, 0, e->stream>>>(p);
+        vc_surface_pass_kernel<true><<<sgrid, 256, 0, e->stream>>>(g, e->g.z_begin, (unsigned)e->plane_words, e->d_block_sums, e->d_color_idx);
         if (color_mode == VC_COLOR_CLOSEST) vc_surface_color_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
         else vc_surface_color_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
         VC_CUDA(e, cudaGetLastError());
@@ -1078,10 +1068,10 @@ int vc_mc_classify(vc_engine* e) {
     const int n_cz = e->g.z_end - cz_begin;
     const int Cw = (e->g.X + 1 + 31) / 32;
     const long long n = (long long)n_cz * (e->g.Y + 1) * Cw;
-    VC_CUDA(e, cudaMemsetAsync(e->d_hist, 0, 256 * sizeof(unsigned long long), e->stream));
+    VC_CUDA(e, cudaMemsetAsync(e->d_hist, 0, 257 * sizeof(unsigned long long), e->stream));
     const long long n_tasks = (long long)n_cz * ((e->g.Y + 1 + VC_MC_ROWS - 1) / VC_MC_ROWS) * ((Cw + 31) / 32);  // one warp each
     long long blocks = (n_tasks + 7) / 8;
-    if (blocks > (long long)e->sm_count * 16) blocks = (long long)e->sm_count * 16;
+    if (blocks > (long long)e->sm_count * 4) blocks = (long long)e->sm_count * 4;  // persistent: warps pull tasks from a counter
     (void)n;
     vc_mc_classify_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(vol_view(e), cz_begin, n_cz, Cw, e->d_hist);
     VC_CUDA(e, cudaGetLastError());
