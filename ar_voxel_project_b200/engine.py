@@ -237,6 +237,12 @@ class VoxelEngine:
         self._check(self._lib.vc_count_occupied(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def surface_count(self):
+        """surface voxels coloured by the last color() call (ColorReconstruction.h:46: occupied and not isInner)"""
+        n = C.c_uint64()
+        self._check(self._lib.vc_surface_count(self._h, C.byref(n)))
+        return int(n.value)
+
     def download_colors(self):
         n = C.c_uint64()
         self._check(self._lib.vc_surface_count(self._h, C.byref(n)))

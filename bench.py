@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-color", action="store_true", help="skip the colour-reconstruction timing (uploads V x H x W x 3 image bytes)")
     ap.add_argument("--uniform-slabs", action="store_true", help="equal-height z-slabs instead of the planner's balanced ones")
     return ap.parse_args()
 
@@ -291,6 +292,22 @@ def run_ours(args):
         mc_tris = allsum(float(nt))
     else:
         mc_tris = None
+    # per-surface-voxel colouring of the carved grid (ColorReconstruction.cpp:22-70) on the same device-resident volume;
+    # the 8UC3 images (V x H x W x 3, hash-coloured) are uploaded outside the timed region
+    color_ms = None
+    if (world == 1 or allgather_ms is not None) and not args.no_color:
+        eng.set_images(w.images_bgr())
+        color_ms = {}
+        for name, mode in (("average", A._lib.VC_COLOR_AVG), ("closest", A._lib.VC_COLOR_CLOSEST)):
+            eng.color(mode)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            eng.color(mode)
+            c1.record()
+            torch.cuda.synchronize()
+            color_ms[name] = allmax(c0.elapsed_time(c1))
+        color_ms["surface_voxels"] = allsum(float(eng.surface_count()))
 
     # end to end through the C ABI with host buffers: (a) the cached bit-packed silhouettes (SURVEY §7-1 cache format,
     # what the CPU arm consumes too) and (b) the 8UC3 undistorted masks as the reference holds them in memory
@@ -381,7 +398,7 @@ def run_ours(args):
                              "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": 2.0 * (Z / world) * Y * Wx * 4 / 3.68e12 * 1e3,
                              "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}; "
                                     "write_only_floor_ms = the two volumes at the 3.68 TB/s a cudaMemset reaches on this GPU (tools/memset_bench.py)"},
-            "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris,
+            "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris, "color_ms": color_ms,
             "e2e": e2e, "e2e_bgr8": e2e_bgr, "gpu_launches": launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
