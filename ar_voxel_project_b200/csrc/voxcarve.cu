@@ -39,8 +39,6 @@ struct vc_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished z-chunks while the next chunk is carving (vc_carve_download)
-    cudaStream_t fill_stream = nullptr;   // vc_fill*_kernel of a fresh VC_EXACT carve, next to vc_carve_bricks
-    cudaEvent_t ev_classified = nullptr, ev_filled = nullptr;
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_mid = false;
     // volumes
@@ -273,9 +271,6 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaEventCreate(&e->ev0));
     VC_CREATE_CUDA(cudaEventCreate(&e->ev1));
     VC_CREATE_CUDA(cudaEventCreate(&e->evm));
-    VC_CREATE_CUDA(cudaStreamCreateWithFlags(&e->fill_stream, cudaStreamNonBlocking));
-    VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_classified, cudaEventDisableTiming));
-    VC_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_filled, cudaEventDisableTiming));
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 257 * sizeof(unsigned long long)));  // [256] = task counter of vc_mc_classify_kernel
     VC_CREATE_CUDA(cudaMalloc(&e->d_filt, VC_MAX_VIEWS * sizeof(VcViewFilter)));
@@ -299,9 +294,6 @@ void vc_destroy(vc_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evm) cudaEventDestroy(e->evm);
-    if (e->ev_classified) cudaEventDestroy(e->ev_classified);
-    if (e->ev_filled) cudaEventDestroy(e->ev_filled);
-    if (e->fill_stream) { cudaStreamSynchronize(e->fill_stream); cudaStreamDestroy(e->fill_stream); }
     for (int c = 0; c < 4; c++) if (e->ev_chunk[c]) cudaEventDestroy(e->ev_chunk[c]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -619,11 +611,12 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
     const long long n_super = (long long)sbx * sby * sbz;
     if (p.nz > 65535) return fail(e, VC_ERR_ARG, "vc_carve: slab of %d planes exceeds the fill grid", p.nz);
-    unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = list length | super-list length, [7] = work counter
+    unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = front list length | super-list length, [7] = work counter | back list length
     unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
     VcBrickParams bp{};
-    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
+    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.n_list_back = d_work + 1; bp.list_cap = (unsigned)n_bricks;
+    bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
     bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
     bp.executed = count ? e->d_scalars + 5 : nullptr;
     bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = p.nz; bp.z_begin = p.z_begin;
@@ -633,40 +626,35 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
     vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
-    // fresh carve: the fill pass skips the listed bricks and runs on its own stream next to the per-voxel kernel, which owns
-    // those bricks' words; otherwise it runs in order (it must apply the flags before the per-voxel kernel reads the state)
-    cudaStream_t fs = fresh ? e->fill_stream : e->stream;
-    if (fresh) {
-        VC_CUDA(e, cudaEventRecord(e->ev_classified, e->stream));
-        VC_CUDA(e, cudaStreamWaitEvent(fs, e->ev_classified, 0));
-    }
     if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
-    if (e->Wx % 4 == 0) {
-        const unsigned Q = (unsigned)e->Wx / 4u;
-        int q_shift = -1;
-        for (int b = 0; b < 31; b++) if (Q == (1u << b)) q_shift = b;
-        const unsigned per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
-        unsigned gy = (unsigned)p.nz;
-        if (fresh) {  // two small blocks per SM, looping over the planes: leaves most of every SM to vc_carve_bricks
-            gy = (2u * (unsigned)e->sm_count + per_plane - 1) / per_plane;
-            if (gy > (unsigned)p.nz) gy = (unsigned)p.nz;
-        }
-        vc_fill4_kernel<<<dim3(per_plane, gy), 256, 0, fs>>>(
-            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, fresh ? 1 : 0, q_shift, p.nz);
-    } else {
-        vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, fs>>>(
-            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, fresh ? 1 : 0);
-    }
-    if (fresh) VC_CUDA(e, cudaEventRecord(e->ev_filled, fs));
     int resident = 0;  // persistent grid: as many blocks of 8 warps as are resident at once
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, vc_carve_bricks<false>, 256, 0) != cudaSuccess || resident < 1) { cudaGetLastError(); resident = 2; }
-    if (fresh && resident > 2) resident--;  // room for the fill pass running next to it
     const unsigned pgrid = (unsigned)e->sm_count * (unsigned)resident;
-    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt);
-    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt);
-    if (fresh) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_filled, 0));  // the carve is complete on e->stream only with the fill
+    // Fill pass (volume words implied by the brick flags).  Fresh carve, rows of whole quads: the first blocks of the persistent
+    // kernel do it themselves, skipping the listed bricks, whose words the work items own.  Otherwise it runs first, in
+    // stream order (it must apply the flags before the per-voxel kernel reads the state; rows of other widths go word by word).
+    VcFillParams fp{};
+    fp.occ = p.occ; fp.seen = p.seen; fp.brick_flags = e->d_brick_flags; fp.super_flags = e->d_super_flags;
+    fp.X = e->g.X; fp.Y = e->g.Y; fp.Wx = e->Wx; fp.nby = nby; fp.pbx = sbx; fp.pby = sby;
+    fp.fresh = fresh ? 1 : 0; fp.skip_listed = fresh ? 1 : 0; fp.nz = p.nz; fp.q_shift = -1; fp.n_fill_blocks = 0;
+    const bool quads = e->Wx % 4 == 0;
+    if (quads) {
+        const unsigned Q = (unsigned)e->Wx / 4u;
+        for (int b = 0; b < 31; b++) if (Q == (1u << b)) fp.q_shift = b;
+        fp.per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
+    }
+    if (fresh && quads) {
+        fp.n_fill_blocks = (unsigned)e->sm_count < pgrid ? (unsigned)e->sm_count : pgrid;  // one per SM (blocks are dealt round-robin)
+    } else if (quads) {
+        vc_fill4_kernel<<<dim3(fp.per_plane, (unsigned)p.nz), 256, 0, e->stream>>>(fp);
+    } else {
+        vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
+            p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, 0);
+    }
+    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work + 1, (unsigned)n_bricks, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt, fp);
+    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work + 1, (unsigned)n_bricks, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt, fp);
     VC_CUDA(e, cudaGetLastError());
-    e->stats.carve_launches += 4;
+    e->stats.carve_launches += (fresh && quads) ? 3 : 4;
     if (n_bricks_out) *n_bricks_out += (uint64_t)n_bricks;
     return VC_OK;
 }
@@ -714,13 +702,14 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->stats.filter_rows = e->stats.filter_slow_rows = e->stats.filter_mismatches = e->stats.subbrick_corner_views = 0;
     e->stats.last_carve_ms = -1.0;  // resolved lazily in vc_get_stats
     if (count_executed) {
-        unsigned long long ex = 0, bc = 0, nl = 0, fl[4] = {0, 0, 0, 0};
+        unsigned long long ex = 0, bc = 0, nl = 0, nw = 0, fl[4] = {0, 0, 0, 0};
         VC_CUDA(e, cudaMemcpyAsync(fl, e->d_scalars + 8, sizeof fl, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&ex, e->d_scalars + 2, sizeof ex, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&bc, e->d_scalars + 5, sizeof bc, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaMemcpyAsync(&nl, e->d_scalars + 6, sizeof nl, cudaMemcpyDeviceToHost, e->stream));
+        VC_CUDA(e, cudaMemcpyAsync(&nw, e->d_scalars + 7, sizeof nw, cudaMemcpyDeviceToHost, e->stream));
         VC_CUDA(e, cudaStreamSynchronize(e->stream));
-        e->stats.bricks_listed = mode == VC_EXACT ? (nl & 0xffffffffull) : 0;
+        e->stats.bricks_listed = mode == VC_EXACT ? (nl & 0xffffffffull) + (nw >> 32) : 0;  // front + back of the work list
         e->stats.executed_voxel_views = ex + (mode == VC_EXACT ? bc : 0);
         e->stats.brick_corner_views = mode == VC_EXACT ? bc : 0;
         if (mode == VC_EXACT) { e->stats.filter_rows = fl[0]; e->stats.filter_slow_rows = fl[1]; e->stats.filter_mismatches = fl[2]; e->stats.subbrick_corner_views = fl[3]; }
@@ -864,7 +853,8 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
     VcBrickParams bp{};
-    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
+    bp.list = e->d_bricks; bp.n_list = d_nlist; bp.n_list_back = d_nlist + 3; bp.list_cap = (unsigned)((long long)nbx * nby * nbz);
+    bp.brick_flags = e->d_brick_flags; bp.sat = e->d_sat;
     bp.super_flags = e->d_super_flags; bp.super_list = e->d_super_list; bp.n_super_list = d_nlist + 1;
     bp.X = e->g.X; bp.Y = e->g.Y; bp.Wx = e->Wx; bp.nz = e->nz; bp.z_begin = e->g.z_begin;
     bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = 0; bp.v1 = e->V; bp.s = e->g.voxel_size;
@@ -873,11 +863,12 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
     vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
-    unsigned int counts[2] = {0, 0};
+    unsigned int counts[4] = {0, 0, 0, 0};  // front length, super-list length, (work counter), back length
     VC_CUDA(e, cudaMemcpyAsync(counts, d_nlist, sizeof counts, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
-    std::vector<VcBrickState> h((size_t)counts[0]);
+    std::vector<VcBrickState> h((size_t)counts[0] + counts[3]);  // the list is filled from both ends (VcBrickParams)
     if (counts[0]) VC_CUDA(e, cudaMemcpy(h.data(), e->d_bricks, (size_t)counts[0] * sizeof(VcBrickState), cudaMemcpyDeviceToHost));
+    if (counts[3]) VC_CUDA(e, cudaMemcpy(h.data() + counts[0], e->d_bricks + (bp.list_cap - counts[3]), (size_t)counts[3] * sizeof(VcBrickState), cudaMemcpyDeviceToHost));
     // cost of a brick layer (8 planes): per-voxel work of its listed bricks (undecided views x voxels) plus a small constant
     // per plane for the classification and fill passes
     std::vector<double> cost((size_t)nbz, 0.0);

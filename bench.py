@@ -23,6 +23,9 @@ import sys
 import threading
 import time
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where the one JSON line belongs
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -181,6 +184,14 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allgather(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     w = Workload(**CONFIGS[args.config])
     X, Y, Z, V = w.X, w.Y, w.Z, w.V
     Wx = (X + 31) // 32
@@ -231,7 +242,7 @@ def run_ours(args):
     clk["sampled_over"] = f"{args.warmup} warm-up + {args.steps} timed + {n_tail} identical untimed steps"
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = allmax(float(np.mean(step_ms)))
-    launches = 4 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_fill4_kernel (absorbs the reset) beside vc_carve_bricks, per step
+    launches = 3 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_carve_bricks (its first blocks do the fill pass, which absorbs the reset), per step
 
     # carve-kernel-only time (events inside vc_carve) and executed voxel-views (separate, untimed counting pass)
     kt, ct = [], []
@@ -264,6 +275,9 @@ def run_ours(args):
     kernel_ms_max = allmax(kernel_ms)
     fine_ms_max = allmax(kernel_ms - classify_ms)
     classify_ms_max = allmax(classify_ms)
+    per_rank = {"carve_ms": allgather(kernel_ms), "classify_ms": allgather(classify_ms),
+                "per_voxel_projections": allgather(float(st["executed_voxel_views"]) - float(st["brick_corner_views"])),
+                "bricks_listed": allgather(float(st["bricks_listed"]))}
 
     # on-demand assembly of the bit-packed grid (NCCL all-gather over NVLink), timed separately
     allgather_ms = None
@@ -344,10 +358,10 @@ def run_ours(args):
         e2e = {"value": nominal_total / s_bits, "unit": UNIT, "h2d_bytes_per_step": int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bits * 1e3,
                "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory",
-               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download", "gpu_launches": 19 * args.steps}
+               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download", "gpu_launches": 15 * args.steps}
         e2e_bgr = {"value": nominal_total / s_bgr, "unit": UNIT, "h2d_bytes_per_step": int(bgr.numel() + w.P.nbytes + w.M.nbytes),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bgr * 1e3,
-                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 20 * args.steps}
+                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 16 * args.steps}
         eng.set_masks_bits(w.mask_bits)
 
     out = None
@@ -382,7 +396,7 @@ def run_ours(args):
             "executed_voxel_views": executed_total, "executed_fraction": executed_total / nominal_total,
             "executed_value": executed_total / (ms_per_step * 1e-3),
             "occupied_voxels": occupied_total, "carve_kernel_ms": kernel_ms_max,
-            "kernels_ms": {"vc_brick_classify_kernel<1>+<0>": classify_ms_max, "vc_carve_bricks (vc_fill4_kernel beside it)": fine_ms_max,
+            "kernels_ms": {"vc_brick_classify_kernel<1>+<0>": classify_ms_max, "vc_carve_bricks (incl. the fill pass)": fine_ms_max,
                            "flat_vc_carve_rows_same_job": flat_ms},
             "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total,
                        "of_which_sub_brick_level": sub_corner_total},
@@ -392,13 +406,13 @@ def run_ours(args):
                          "traffic": traffic, "algorithmic_bytes": exec_rank / 8.0 + 2.0 * bricks_listed / world * 2048 / 8,
                          "kernel": "vc_carve_bricks",
                          "how": f"projections of one vc_carve_bricks launch ({exec_rank:.4g}: per-voxel + sub-brick corners) x {F_ALG:.0f} FLOP / its time "
-                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve; the fill pass runs beside it); peak = FFMA microbenchmark on this GPU "
+                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve; the kernel's first blocks also do the fill pass); peak = FFMA microbenchmark on this GPU "
                                 f"(vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s. The kernel is issue-bound, see profiles/"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": 2.0 * (Z / world) * Y * Wx * 4 / 3.68e12 * 1e3,
                              "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}; "
                                     "write_only_floor_ms = the two volumes at the 3.68 TB/s a cudaMemset reaches on this GPU (tools/memset_bench.py)"},
-            "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris, "color_ms": color_ms,
+            "allgather_ms": allgather_ms, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris, "color_ms": color_ms, "per_rank": per_rank,
             "e2e": e2e, "e2e_bgr8": e2e_bgr, "gpu_launches": launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:

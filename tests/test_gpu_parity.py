@@ -240,6 +240,39 @@ def test_mc_classify_random_volumes(A, oracle, dims):
         assert hist.sum() == (X + 1) * (Y + 1) * (Z + 1)
 
 
+@pytest.mark.parametrize("dims", [(1088, 20, 3), (2100, 19, 2), (150, 300, 3), (160, 40, 33)])
+def test_mc_and_surface_wide_and_ragged_volumes(A, oracle, dims):
+    """shapes the warp-cooperative consumer kernels have to get right: more than 32 voxel-word columns (a warp's lane 0 then
+    has a left neighbour word), X % 32 == 0 (cell c = X in a word of its own), rows that do not fill a thread's 4 words
+    (Wx = 5), planes spanning several 1024-word blocks; random noise, solid boxes (faces parallel to x: 32 mixed cells per
+    word) and an empty / a full grid.  Surface = occupied & !isInner is checked through vc_color's record indices."""
+    from ar_voxel_project_b200.synth import Workload, pack_bits
+    X, Y, Z = dims
+    rng = np.random.default_rng(X + 7 * Y + 131 * Z)
+    w = Workload(16, 2, 64, 48, seed=4)   # any two views: only the voxel set of the records is compared here
+    vols = [rng.random((Z, Y, X)) < 0.5, rng.random((Z, Y, X)) < 0.97, np.zeros((Z, Y, X), bool), np.ones((Z, Y, X), bool)]
+    box = np.zeros((Z, Y, X), bool)
+    box[Z // 3:, Y // 4:Y - Y // 4, 5:X - 3] = True
+    box[:, Y // 2, X // 2:X // 2 + 70] = False
+    vols.append(box)
+    for vol in vols:
+        occ = pack_bits(vol)
+        with A.VoxelEngine(X, Y, Z, 1e-3) as e:
+            e.set_views(w.P, w.W, w.H, w.M)
+            e.set_images(w.images_bgr())
+            e.upload_volumes(occ, occ)
+            e.mc_classify()
+            hist, na, nt = e.download_mc()
+            e.color(A._lib.VC_COLOR_AVG)
+            idx, _ = e.download_colors()
+        rh, rna, rnt = oracle.mc_classify(X, Y, Z, occ)
+        assert np.array_equal(hist, rh) and (na, nt) == (rna, rnt)
+        pad = np.pad(vol, 1)
+        inner = pad[:-2, 1:-1, 1:-1] & pad[2:, 1:-1, 1:-1] & pad[1:-1, :-2, 1:-1] & pad[1:-1, 2:, 1:-1] & pad[1:-1, 1:-1, :-2] & pad[1:-1, 1:-1, 2:]
+        ref_idx = np.flatnonzero((vol & ~inner).ravel()).astype(np.uint64)   # flatten = x + X*(y + Y*z) is the C order of [z][y][x]
+        assert np.array_equal(idx, ref_idx)
+
+
 def test_reference_named_api_on_model(A, oracle, golden):
     """carve / reconstructAvgColor / marchingCubesClassify on a host Model, as main.cpp:260-303 calls them"""
     vs = A.ViewSet.from_npz(os.path.join(GOLDEN, "box_views.npz"))
