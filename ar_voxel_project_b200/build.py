@@ -37,19 +37,22 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: experiment variants (-D switches) built next to the product library, never loaded by default"""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = out or LIB
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libvoxcarve.so")
-    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
+    with open(target[:-3] + ".ptxas.log" if out else os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

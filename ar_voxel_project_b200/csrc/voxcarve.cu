@@ -644,7 +644,10 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
         fp.per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
     }
     if (fresh && quads) {
-        fp.n_fill_blocks = (unsigned)e->sm_count < pgrid ? (unsigned)e->sm_count : pgrid;  // one per SM (blocks are dealt round-robin)
+#ifndef VC_FILL_PER_SM
+#define VC_FILL_PER_SM 1
+#endif
+        fp.n_fill_blocks = (unsigned)e->sm_count * VC_FILL_PER_SM < pgrid ? (unsigned)e->sm_count * VC_FILL_PER_SM : pgrid;  // one per SM (blocks are dealt round-robin)
     } else if (quads) {
         vc_fill4_kernel<<<dim3(fp.per_plane, (unsigned)p.nz), 256, 0, e->stream>>>(fp);
     } else {

@@ -12,7 +12,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C4")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--lib", default=None, help="experiment variant of libvoxcarve.so (see build.build(out=...))")
 a = ap.parse_args()
+if a.lib:
+    import ar_voxel_project_b200._lib as L
+    L.LIB_PATH = os.path.abspath(a.lib)
 w = Workload(**CONFIGS[a.config])
 with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
     e.set_views(w.P, w.W, w.H, w.M)
