@@ -148,6 +148,13 @@ void set_mask_window(vc_engine* e, bool on) {
     cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev);
     if (max_win <= 0 || persist_max <= 0 || !e->d_mask) { e->stats.l2_persist_bytes = 0; return; }
     size_t bytes = e->mask_bytes < (size_t)max_win ? e->mask_bytes : (size_t)max_win;
+    // Off unless VOXCARVE_L2_PERSIST_MB=<cap in MB> asks for it.  Measured on B200: the silhouettes stay L2-resident on their
+    // own (C4, 18.7 MB: 0.50 ms with and without the window), and a large persisting carve-out starves everything else -
+    // C5 (74.6 MB of masks): 4.81 ms with the full window, 3.07 ms capped at 48 MB, 2.36 ms at 24 MB, 2.06 ms without.
+    const char* cap = getenv("VOXCARVE_L2_PERSIST_MB");
+    const long cap_mb = cap ? atol(cap) : 0;
+    if (cap_mb <= 0) { e->stats.l2_persist_bytes = 0; return; }
+    if ((size_t)cap_mb << 20 < (size_t)persist_max) persist_max = (int)((size_t)cap_mb << 20);
     if (on) {
         size_t carve_out = bytes < (size_t)persist_max ? bytes : (size_t)persist_max;
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve_out);
@@ -644,12 +651,14 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
         fp.per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
     }
     if (fresh && quads) {
-#ifndef VC_FILL_PER_SM
-#define VC_FILL_PER_SM 1
-#endif
-        fp.n_fill_blocks = (unsigned)e->sm_count * VC_FILL_PER_SM < pgrid ? (unsigned)e->sm_count * VC_FILL_PER_SM : pgrid;  // one per SM (blocks are dealt round-robin)
+        // one fill block per SM (blocks are dealt round-robin), more when a block would otherwise walk more than ~64 brick layers
+        const unsigned long long units = (unsigned long long)fp.per_plane * (unsigned)nbz;
+        unsigned per_sm = (unsigned)((units + 64ull * e->sm_count - 1) / (64ull * e->sm_count));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > (unsigned)resident / 2) per_sm = resident >= 2 ? (unsigned)resident / 2 : 1;
+        fp.n_fill_blocks = (unsigned)e->sm_count * per_sm < pgrid ? (unsigned)e->sm_count * per_sm : pgrid;
     } else if (quads) {
-        vc_fill4_kernel<<<dim3(fp.per_plane, (unsigned)p.nz), 256, 0, e->stream>>>(fp);
+        vc_fill4_kernel<<<dim3(fp.per_plane, (unsigned)nbz), 256, 0, e->stream>>>(fp);  // one block per (256 quads, brick layer)
     } else {
         vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
             p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, 0);

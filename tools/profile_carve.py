@@ -26,7 +26,7 @@ with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
         e.carve(a.mode)
         e.synchronize()
         st = e.stats()
-        print("carve ms", st["last_carve_ms"], "of which classify+fill", st["last_classify_ms"])
+        print("carve ms", st["last_carve_ms"], "of which classify+fill", st["last_classify_ms"], "L2 persisting bytes", st["l2_persist_bytes"])
     e.reset()
     e.carve(a.mode, count_executed=True)
     st = e.stats()
