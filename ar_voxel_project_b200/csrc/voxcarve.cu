@@ -69,7 +69,7 @@ struct vc_engine {
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
     // colour / mc results
-    unsigned long long *d_block_sums = nullptr, *d_scalars = nullptr;  // scalars: [0]=total surf, [1]=n_list(u32), [2]=executed, [3..4]=popcounts
+    unsigned long long *d_block_sums = nullptr, *d_scalars = nullptr;  // scalars: [2]=executed, [3..4]=popcounts, [5]=corner projections, [6]=work-list front | super-list lengths, [7]=work counter | work-list back length, [8..11]=filter statistics
     unsigned long long* d_color_idx = nullptr;
     uchar4* d_color_rgbn = nullptr;
     unsigned long long n_surface = 0, color_capacity = 0;  // colour record buffers are grow-only

@@ -71,7 +71,7 @@ enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1, VC_MASK_BGR8_RAW = 2 /
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
     double last_classify_ms;       /* of which: the two brick-classification kernels (0 for the flat modes); the rest is the per-voxel
-                                      kernel with, on a fresh carve, the fill pass running beside it */
+                                      kernel, whose first blocks also run the fill pass on a fresh carve */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
     uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */
@@ -79,7 +79,8 @@ typedef struct vc_stats {
     uint64_t bricks_listed;
     uint64_t flood_rounds;         /* sweep rounds of the last vc_fast_carve */
     uint64_t carve_launches;       /* kernel launches issued by this engine so far */
-    uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the access-policy window */
+    uint64_t l2_persist_bytes;     /* bytes of the mask set pinned by the L2 access-policy window; 0 unless the environment
+                                      variable VOXCARVE_L2_PERSIST_MB enables it (measured neutral to harmful on B200) */
     /* per-voxel f32 filter of VC_EXACT (counting runs only): 32-voxel rows evaluated, rows that needed the exact f64
      * re-evaluation, and filter decisions that disagreed with the exact evaluation (every decision is cross-checked
      * in a counting run; anything but 0 is a bug) */
