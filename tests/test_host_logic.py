@@ -92,3 +92,27 @@ def test_view_cache_loads_and_matches_calibration():
     assert abs(float(z["K32"][0, 0]) - 496.50601) < 1e-3 and z["mask_bits"].shape == (8, 480, 20)   # cameracalibration.yml, 640/32 words
     with pytest.raises(ValueError):
         ViewSet(vs.P, vs.M, 640, 480, mask_bits=vs.mask_bits[:3])                        # main.cpp:228-231 count mismatch
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host alone (no GPU): one JSON line with the contract's keys, the CPU restatement
+    as the thing measured, zero transfer bytes; under torchrun every rank but 0 exits 0 without printing."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "C3", "--steps", "1", "--warmup", "0",
+           "--cpu-seconds", "0.2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "voxel_view_projections_per_s" and d["unit"] == "voxel-views/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("synthetic 512x512x512 x 36 views")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
