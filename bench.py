@@ -23,8 +23,16 @@ import sys
 import threading
 import time
 
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where the one JSON line belongs
+# stdout carries exactly ONE line, the JSON result: library chatter written to file descriptor 1 (NCCL prints its version banner
+# there) is sent to stderr instead, and emit() writes the result to the real stdout
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
 
 import numpy as np
 
@@ -142,7 +150,7 @@ def run_reference(args):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference C++ cannot be built here (needs OpenCV C++ + Eigen); this is oracle/, its pinned C restatement"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -423,7 +431,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     return 0
 
 
