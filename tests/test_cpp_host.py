@@ -25,6 +25,19 @@ def test_host_layer_compiles_without_opencv(tmp_path, lib_built):
                            os.path.join(ROOT, "include", "voxcarve_shim.hpp")])
 
 
+@pytest.mark.parametrize("replace_post", [False, True])
+def test_opencv_shim_compiles_against_the_reference_interface(replace_post):
+    """include/voxcarve_shim.hpp is the file a maintainer drops into the reference; OpenCV and Eigen are absent here, so it is
+    type-checked against interface-only stand-ins of the headers it includes (tests/cpp/shim_stubs: the reference's Model,
+    Benchmark, estimatePoseFromImage, marchingCubes / applyClosure prototypes; cv::Mat, Eigen vectors) from a caller written
+    like main.cpp:260-303."""
+    stubs = os.path.join(ROOT, "tests", "cpp", "shim_stubs")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", stubs, "-I", os.path.join(ROOT, "include")]
+    if replace_post:
+        cmd.append("-DVOXCARVE_SHIM_REPLACE_POSTPROCESSING")
+    subprocess.check_call(cmd + [os.path.join(ROOT, "tests", "cpp", "shim_user.cpp")])
+
+
 @pytest.mark.gpu
 def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
     from ar_voxel_project_b200.api import ViewSet
