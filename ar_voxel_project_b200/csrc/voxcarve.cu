@@ -21,7 +21,8 @@ namespace {
 std::string g_create_error;
 std::mutex g_const_mutex;
 // which (engine uid, views version) currently owns c_view / c_cam on each device
-struct ConstOwner { unsigned long long uid = 0, version = 0; };
+// and an event recorded after the owner's last launch that reads them: a new owner waits for it before overwriting the symbols
+struct ConstOwner { unsigned long long uid = 0, version = 0; cudaEvent_t last_use = nullptr; bool used = false; };
 ConstOwner g_const_owner[64];
 unsigned long long g_next_uid = 1;
 
@@ -121,6 +122,10 @@ int ensure_constants(vc_engine* e) {
     std::lock_guard<std::mutex> lk(g_const_mutex);
     ConstOwner& o = g_const_owner[e->g.device & 63];
     if (o.uid == e->uid && o.version == e->views_version) return VC_OK;
+    // c_view / c_cam / c_filt are per-device symbols shared by every engine on this GPU: kernels of the previous owner (another
+    // engine, or this one with older views) may still be reading them on another stream
+    if (o.used && o.last_use) VC_CUDA(e, cudaEventSynchronize(o.last_use));
+    o.used = false;
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_view, e->h_view.data(), sizeof(VcViewConst) * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_cam, e->h_cam.data(), sizeof(float) * 4 * e->V, 0, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyToSymbolAsync(c_filt, e->h_filt.data(), sizeof(VcViewFilter) * e->V, 0, cudaMemcpyHostToDevice, e->stream));
@@ -128,6 +133,17 @@ int ensure_constants(vc_engine* e) {
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     o.uid = e->uid;
     o.version = e->views_version;
+    return VC_OK;
+}
+
+// call after the last launch of an entry point that reads the view constants
+int constants_used(vc_engine* e) {
+    std::lock_guard<std::mutex> lk(g_const_mutex);
+    ConstOwner& o = g_const_owner[e->g.device & 63];
+    if (o.uid != e->uid) return VC_OK;
+    if (!o.last_use) VC_CUDA(e, cudaEventCreateWithFlags(&o.last_use, cudaEventDisableTiming));
+    VC_CUDA(e, cudaEventRecord(o.last_use, e->stream));
+    o.used = true;
     return VC_OK;
 }
 
@@ -307,7 +323,7 @@ void vc_destroy(vc_engine* e) {
     {
         std::lock_guard<std::mutex> lk(g_const_mutex);
         ConstOwner& o = g_const_owner[e->g.device & 63];
-        if (o.uid == e->uid) o = ConstOwner();
+        if (o.uid == e->uid) { o.uid = 0; o.version = 0; o.used = false; }  // the stream was synchronised above; the event is kept for the device
     }
     delete e;
 }
@@ -707,6 +723,8 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         if (rc) return rc;
     }
     VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    rc = constants_used(e);
+    if (rc) return rc;
     set_mask_window(e, false);
     e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)(view_end - view_begin);
     e->stats.executed_voxel_views = 0;
@@ -775,6 +793,8 @@ int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* 
     }
     e->reset_pending = false;
     VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    rc = constants_used(e);
+    if (rc) return rc;
     set_mask_window(e, false);
     e->stats.nominal_voxel_views = (uint64_t)e->g.X * e->g.Y * e->nz * (uint64_t)e->V;
     e->stats.executed_voxel_views = 0;
@@ -1034,6 +1054,8 @@ int vc_color(vc_engine* e, int32_t color_mode) {
         if (color_mode == VC_COLOR_CLOSEST) vc_surface_color_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
         else vc_surface_color_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(p);
         VC_CUDA(e, cudaGetLastError());
+        rc = constants_used(e);
+        if (rc) return rc;
     }
     e->have_colors = true;
     return VC_OK;

@@ -26,25 +26,81 @@
 #include "Model.h"
 #include "PoseEstimation.h"
 #include "aruco_samples_utility.hpp"
+// the prototypes this file defines, with their default arguments (VoxelCarving.h:19,31; ColorReconstruction.h:131,142):
+// main.cpp:7-8 includes them before anything else here, so the definitions below must not restate a default
+#include "VoxelCarving.h"
+#include "ColorReconstruction.h"
 #include "voxcarve_host.hpp"
 
 namespace vc {
 
+// What a cached ViewCache was built from: every image / mask buffer (address, geometry and a sampled fingerprint of its
+// bytes), the camera matrix and the distortion coefficients.  The reference recomputes poses and undistortions on every
+// call (VoxelCarving.cpp:25,36; ColorReconstruction.h:17-28); the cache may only be reused when all of this is unchanged.
+struct ViewCacheKey {
+    std::vector<const void*> ptr;
+    std::vector<int> geom;           // rows, cols per buffer
+    std::vector<uint64_t> sample;    // sampled content fingerprint per buffer
+    std::vector<double> calib;       // K (row-major) then dist
+    bool operator==(const ViewCacheKey& o) const { return ptr == o.ptr && geom == o.geom && sample == o.sample && calib == o.calib; }
+};
+inline uint64_t sampleBytes(const cv::Mat& m) {  // every 61st 8-byte word of a continuous buffer (all of a tiny one)
+    uint64_t h = 1469598103934665603ull;
+    if (!m.isContinuous() || !m.data) return h;
+    const size_t n = (size_t)m.rows * m.cols * 3 / 8;
+    const size_t stride = n > 4096 ? 61 : 1;
+    for (size_t i = 0; i < n; i += stride) {
+        uint64_t w;
+        std::memcpy(&w, m.data + i * 8, 8);
+        h = (h ^ w) * 1099511628211ull;
+    }
+    return h;
+}
+inline ViewCacheKey viewCacheKey(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, std::vector<cv::Mat>& images, std::vector<cv::Mat>& masks) {
+    ViewCacheKey k;
+    for (std::vector<cv::Mat>* set : {&images, &masks})
+        for (cv::Mat& m : *set) {
+            k.ptr.push_back((const void*)m.data);
+            k.geom.push_back(m.rows);
+            k.geom.push_back(m.cols);
+            k.sample.push_back(sampleBytes(m));
+        }
+    cv::Mat K64, D64;
+    cameraMatrix.convertTo(K64, CV_64F);
+    distCoeffs.convertTo(D64, CV_64F);
+    for (int i = 0; i < (int)K64.total(); i++) k.calib.push_back(K64.at<double>(i));
+    for (int i = 0; i < (int)D64.total(); i++) k.calib.push_back(D64.at<double>(i));
+    return k;
+}
+struct ViewCacheSlot {
+    ViewCache cache;
+    ViewCacheKey key;
+    bool valid = false;
+};
+inline ViewCacheSlot& viewCacheSlot() {
+    static ViewCacheSlot slot;
+    return slot;
+}
+// Drop the cached poses / buffers, e.g. after re-segmenting masks in place (same buffers, same sampled bytes).
+inline void invalidateViewCache() { viewCacheSlot() = ViewCacheSlot(); }
+
 // Everything the reference recomputes per call, computed once: pose per image
 // (estimatePoseFromImage + inv, VoxelCarving.cpp:25-26), P = intr(CV_32F) * pose(3x4) (:19,29-30,41).
 // Masks / images are handed over RAW: the engine runs cv::undistort (:36, ColorReconstruction.h:23) on the device,
-// bit-exact with OpenCV's 8UC3 path.  Keyed on the image data pointers so that
-// carve() followed by reconstruct*Color() on the same vectors (main.cpp:260-288) estimates poses once.
+// bit-exact with OpenCV's 8UC3 path.  The cache always carries the images, so that carve() followed by
+// reconstruct*Color() on the same vectors (main.cpp:260-288) estimates the poses once.
 inline const ViewCache& cachedViews(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, std::vector<cv::Mat>& images,
-                                    std::vector<cv::Mat>& masks, bool need_images) {
-    static ViewCache cache;
-    static const void* key = nullptr;
-    static size_t key_n = 0;
-    static bool has_images = false;
-    const void* k = images.empty() ? nullptr : (const void*)images[0].data;
-    if (k == key && key_n == images.size() && (has_images || !need_images)) return cache;
-    cache = ViewCache();
+                                    std::vector<cv::Mat>& masks) {
+    ViewCacheSlot& slot = viewCacheSlot();
+    ViewCacheKey key = viewCacheKey(cameraMatrix, distCoeffs, images, masks);
+    if (slot.valid && slot.key == key) return slot.cache;
+    slot = ViewCacheSlot();
+    ViewCache& cache = slot.cache;
     cache.V = (int)images.size();
+    if (images.empty() || masks.size() != images.size()) {  // the reference's loops simply do not run (main.cpp:228-231 checks the counts)
+        cache.V = 0;
+        return cache;
+    }
     cache.W = images[0].cols;
     cache.H = images[0].rows;
     cv::Mat intr = cameraMatrix.clone();
@@ -63,40 +119,41 @@ inline const ViewCache& cachedViews(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, 
         cache.P.insert(cache.P.end(), (float*)P.data, (float*)P.data + 12);
         const cv::Mat um = masks[i].isContinuous() ? masks[i] : masks[i].clone();
         cache.mask_bgr.insert(cache.mask_bgr.end(), um.data, um.data + (size_t)um.rows * um.cols * 3);
-        if (need_images) {
-            const cv::Mat ui = images[i].isContinuous() ? images[i] : images[i].clone();
-            cache.images_bgr.insert(cache.images_bgr.end(), ui.data, ui.data + (size_t)ui.rows * ui.cols * 3);
-        }
+        const cv::Mat ui = images[i].isContinuous() ? images[i] : images[i].clone();
+        cache.images_bgr.insert(cache.images_bgr.end(), ui.data, ui.data + (size_t)ui.rows * ui.cols * 3);
     }
-    key = k;
-    key_n = images.size();
-    has_images = need_images;
+    slot.key = std::move(key);
+    slot.valid = true;
     return cache;
 }
 }  // namespace vc
 
 inline void carve(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, Model& model, std::vector<cv::Mat>& images,
-                  std::vector<cv::Mat>& masks, bool intermediateMeshes = false) {
+                  std::vector<cv::Mat>& masks, bool intermediateMeshes) {  // default (= false) lives in VoxelCarving.h:19
     Benchmark::GetInstance().LogCarving(true);
-    vc::carve(vc::cachedViews(cameraMatrix, distCoeffs, images, masks, false), model, intermediateMeshes);
+    const vc::ViewCache& views = vc::cachedViews(cameraMatrix, distCoeffs, images, masks);
+    if (views.V > 0) vc::carve(views, model, intermediateMeshes);  // writes out/intermediate/image_<i>_mesh.off like VoxelCarving.cpp:65-68
     Benchmark::GetInstance().LogCarving(false);
 }
 inline void fastCarve(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, Model& model, std::vector<cv::Mat>& images,
                       std::vector<cv::Mat>& masks) {
     Benchmark::GetInstance().LogCarving(true);
-    vc::fastCarve(vc::cachedViews(cameraMatrix, distCoeffs, images, masks, false), model);
+    const vc::ViewCache& views = vc::cachedViews(cameraMatrix, distCoeffs, images, masks);
+    if (views.V > 0) vc::fastCarve(views, model);
     Benchmark::GetInstance().LogCarving(false);
 }
 inline void reconstructClosestColor(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, Model& model, std::vector<cv::Mat>& images,
                                     std::vector<cv::Mat>& masks) {
     Benchmark::GetInstance().LogColoring(true);
-    vc::reconstructClosestColor(vc::cachedViews(cameraMatrix, distCoeffs, images, masks, true), model);
+    const vc::ViewCache& views = vc::cachedViews(cameraMatrix, distCoeffs, images, masks);
+    if (views.V > 0) vc::reconstructClosestColor(views, model);
     Benchmark::GetInstance().LogColoring(false);
 }
 inline void reconstructAvgColor(cv::Mat& cameraMatrix, cv::Mat& distCoeffs, Model& model, std::vector<cv::Mat>& images,
                                 std::vector<cv::Mat>& masks) {
     Benchmark::GetInstance().LogColoring(true);
-    vc::reconstructAvgColor(vc::cachedViews(cameraMatrix, distCoeffs, images, masks, true), model);
+    const vc::ViewCache& views = vc::cachedViews(cameraMatrix, distCoeffs, images, masks);
+    if (views.V > 0) vc::reconstructAvgColor(views, model);
     Benchmark::GetInstance().LogColoring(false);
 }
 

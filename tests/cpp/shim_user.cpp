@@ -1,6 +1,16 @@
 // A translation unit that uses the shim the way main.cpp:260-303 uses the reference (type check only, never linked).
 #include <string>
 #include <vector>
+// the reference's headers in the order main.cpp:4-11 includes them (stand-ins with the same prototypes and default
+// arguments), THEN the shim - exactly what INTEGRATION.md step 3 prescribes
+#include "Calibration.h"
+#include "PoseEstimation.h"
+#include "Segmentation.h"
+#include "VoxelCarving.h"
+#include "ColorReconstruction.h"
+#include "MarchingCubes.h"
+#include "Postprocessing3d.h"
+#include "Benchmark.h"
 
 #include "voxcarve_shim.hpp"
 

@@ -523,14 +523,40 @@ def test_carve_download_chunked_equals_plain(A, oracle, dims):
     assert np.array_equal(occ[Z // 2:Z // 2 + 3], ro) and np.array_equal(seen[Z // 2:Z // 2 + 3], rs)
 
 
+def _oracle_planes(oracle, w, X, Y, Z, planes, occ, seen):
+    """compare the given z-planes (grouped into contiguous runs) of occ / seen with the oracle; returns #planes compared"""
+    planes = sorted({int(z) for z in planes if 0 <= z < Z})
+    runs, a = [], 0
+    while a < len(planes):
+        b = a
+        while b + 1 < len(planes) and planes[b + 1] == planes[b] + 1:
+            b += 1
+        runs.append((planes[a], planes[b] + 1))
+        a = b + 1
+    for z0, z1 in runs:
+        ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z1, nthreads=0)
+        assert np.array_equal(occ[z0:z1], ro), f"occupied differs from the oracle in planes [{z0},{z1})"
+        assert np.array_equal(seen[z0:z1], rs), f"seen differs from the oracle in planes [{z0},{z1})"
+    return len(planes)
+
+
+def _object_edge_planes(occ):
+    """first / last z-plane that still holds an occupied voxel seen by some view: the silhouette-edge planes of the object"""
+    nz = np.flatnonzero(occ.reshape(occ.shape[0], -1).any(axis=1))
+    return (int(nz[0]), int(nz[-1])) if len(nz) else (0, 0)
+
+
 def test_config4_1024cubed_full_size_properties(A, oracle):
     """BASELINE configs[3] at full size (1024^3 x 72 views x 1920x1080) on one GPU: VC_EXACT == VC_EXACT_FLAT bit for bit,
-    carved => seen, and three 2-plane slabs against the oracle."""
+    carved => seen, every filter decision cross-checked, and >= 64 z-planes against the oracle: the grid's first / last planes,
+    every boundary +-1 the slab planner picks for 2, 4 and 8 GPUs, the planes where the object starts / ends, and a regular
+    stride through the volume."""
     from ar_voxel_project_b200.synth import Workload, CONFIGS
     w = Workload(**CONFIGS["C4"])
     with A.VoxelEngine(1024, 1024, 1024, w.s) as e:
         e.set_views(w.P, w.W, w.H)
         e.set_masks_bits(w.mask_bits)
+        bounds = sorted({b for n in (2, 4, 8) for b in e.plan_slabs(n)})
         occ, seen = e.carve_download()
         n_occ, n_seen = e.count_occupied()
         e.reset()
@@ -544,9 +570,63 @@ def test_config4_1024cubed_full_size_properties(A, oracle):
         assert np.array_equal(e.download_occupied(), occ) and np.array_equal(e.download_seen(), seen)
     assert ((~occ) & (~seen)).max() == 0
     assert 0.02 < n_occ / 1024 ** 3 < 0.25 and n_seen <= 1024 ** 3
-    for z0 in (0, 511, 1022):
-        ro, rs = oracle.carve(1024, 1024, 1024, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z0 + 2, nthreads=0)
-        assert np.array_equal(occ[z0:z0 + 2], ro) and np.array_equal(seen[z0:z0 + 2], rs)
+    # planes that still hold voxels no view carved because no view sees them do not count as the object: use the seen ones
+    lo, hi = _object_edge_planes(occ & seen)
+    planes = {0, 1, 1022, 1023, 511, 512}
+    planes |= {b + d for b in bounds for d in (-1, 0)}
+    planes |= {z + d for z in (lo, hi) for d in (-2, -1, 0, 1, 2)}
+    planes |= set(range(5, 1024, 24))
+    n = _oracle_planes(oracle, w, 1024, 1024, 1024, planes, occ, seen)
+    assert n >= 64, n
+
+
+def test_config5_2048cubed_full_size_properties(A, oracle):
+    """BASELINE configs[4] at full size (2048^3 x 72 views x 3840x2160; 1 GiB per bit volume, 2.4 GB of summed-area tables)
+    on one GPU.  The reference cannot even index this grid (`int flatten`, Model.h:104-106), so the oracle slab check is the
+    only possible pin: VC_EXACT == VC_EXACT_FLAT bit for bit over the whole volume, carved => seen, and two-plane oracle slabs
+    at z = 0, the middle (1023/1024), the end (2046), the planner's 8-GPU boundaries and the object's first / last planes."""
+    from ar_voxel_project_b200.synth import Workload, CONFIGS
+    w = Workload(**CONFIGS["C5"])
+    N = 2048
+    with A.VoxelEngine(N, N, N, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        bounds = e.plan_slabs(8)
+        e.carve()
+        occ, seen = e.download_occupied(), e.download_seen()
+        n_occ, n_seen = e.count_occupied()
+        e.reset()
+        e.carve(2)
+        flat_occ = e.download_occupied()
+        assert np.array_equal(flat_occ, occ)
+        del flat_occ
+        flat_seen = e.download_seen()
+        assert np.array_equal(flat_seen, seen)
+        del flat_seen
+        e.reset()
+        o2, s2 = e.carve_download()   # the chunked path crosses 2^31 bits per chunk too
+        assert np.array_equal(o2, occ) and np.array_equal(s2, seen)
+        del o2, s2
+        e.mc_classify()
+        hist, na, nt = e.download_mc()
+    assert int(hist.sum()) == (N + 1) ** 3 and nt > 0
+    assert ((~occ) & (~seen)).max() == 0
+    assert 0.02 < n_occ / N ** 3 < 0.25 and n_seen <= N ** 3
+    assert int(np.unpackbits(occ[1000:1002].view(np.uint8)).sum()) > 0
+    lo, hi = _object_edge_planes(occ & seen)
+    planes = set()
+    for z0 in [0, 1023, 2046, lo - 1, hi] + [b - 1 for b in bounds[1:-1]]:
+        planes |= {z0, z0 + 1}
+    n = _oracle_planes(oracle, w, N, N, N, planes, occ, seen)
+    assert n >= 16, n
+    # the cube-index histogram of a two-plane slab against the oracle's (cells between planes 1023 and 1024 are interior to it)
+    ro = occ[1022:1026]
+    rh, _, _ = oracle.mc_classify(N, N, 4, np.ascontiguousarray(ro))
+    with A.VoxelEngine(N, N, 4, w.s) as e2:
+        e2.upload_volumes(np.ascontiguousarray(ro), np.zeros_like(ro))
+        e2.mc_classify()
+        h2, _, _ = e2.download_mc()
+    assert np.array_equal(h2, rh)
 
 
 def test_device_undistort_matches_cv2_kat_and_raw_mask_path(A, oracle, golden):
