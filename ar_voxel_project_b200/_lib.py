@@ -67,6 +67,7 @@ SIGNATURES = {
     "vc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "vc_dense_upload": (C.c_int, [_P, _P]),
     "vc_dense_from_volumes": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "vc_dense_apply_carved": (C.c_int, [_P]),
     "vc_dense_closure": (C.c_int, [_P, C.c_int32]),
     "vc_dense_download": (C.c_int, [_P, _P]),
     "vc_mc_mesh": (C.c_int, [_P, C.c_float, C.POINTER(C.c_uint64)]),

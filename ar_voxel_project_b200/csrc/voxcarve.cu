@@ -29,7 +29,8 @@ unsigned long long g_next_uid = 1;
 }  // namespace
 
 extern "C" {
-static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream);
+static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream,
+                                    double** ir_buf = nullptr, size_t* ir_count = nullptr);
 }
 
 struct vc_engine {
@@ -66,6 +67,13 @@ struct vc_engine {
     uint8_t* d_super_flags = nullptr;    // ... per super-brick
     unsigned int* d_super_list = nullptr;
     bool reset_pending = false;          // vc_reset not yet materialised (a VC_EXACT carve folds it into its fill pass)
+    bool carved_implies_seen = true;     // invariant of every state the engine produces; uploaded volumes may break it (vc_upload_volumes)
+    // grow-only scratch shared by vc_fast_carve (flood volume), vc_mc_mesh (column counts), raw uploads and the
+    // carved-but-unseen path of vc_carve: none of them runs concurrently with another on this engine's stream
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double* d_undist_ir = nullptr;       // per-stripe inverse camera matrices of the device cv::undistort (grow-only)
+    size_t undist_ir_count = 0;
     int sm_count = 148;
     uint8_t* d_images = nullptr;
     size_t mask_bytes = 0;
@@ -81,7 +89,7 @@ struct vc_engine {
     float4 *d_dense = nullptr, *d_dense_tmp = nullptr;
     float* d_mesh_verts = nullptr;
     uint32_t* d_mesh_rgb = nullptr;
-    unsigned long long n_mesh_tris = 0;
+    unsigned long long n_mesh_tris = 0, mesh_capacity = 0;
     bool have_dense = false, have_mesh = false;
     bool have_calib = false;
     double calib_K[9] = {0}, calib_dist[8] = {0};
@@ -115,6 +123,24 @@ int fail(vc_engine* e, int code, const char* fmt, ...) {
 int bind_device(vc_engine* e) {
     VC_CUDA(e, cudaSetDevice(e->g.device));
     return VC_OK;
+}
+
+// grow-only scratch; the caller owns it until its work on e->stream is enqueued (stream order protects the next user)
+int ensure_scratch(vc_engine* e, size_t bytes, void** out) {
+    if (e->scratch_bytes < bytes) {
+        VC_CUDA(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_scratch); e->d_scratch = nullptr; e->scratch_bytes = 0;
+        VC_CUDA(e, cudaMalloc(&e->d_scratch, bytes));
+        e->scratch_bytes = bytes;
+    }
+    *out = e->d_scratch;
+    return VC_OK;
+}
+
+bool host_pinned(const void* p) {  // page-locked (cudaHostAlloc / cudaHostRegister) host memory?
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 // upload this engine's view constants if another engine (or an older version) owns them
@@ -313,6 +339,7 @@ void vc_destroy(vc_engine* e) {
     cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
+    cudaFree(e->d_scratch); cudaFree(e->d_undist_ir);
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -401,12 +428,12 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
         uint8_t* d_tmp = e->d_bgr_tmp;
         VC_CUDA(e, cudaMemcpyAsync(d_tmp, masks, bytes, cudaMemcpyHostToDevice, e->stream));
         if (format == VC_MASK_BGR8_RAW) {  // cv::undistort(mask, undist_mask, cameraMatrix, distCoeffs) (VoxelCarving.cpp:36)
-            uint8_t* d_und = nullptr;
-            VC_CUDA(e, cudaMalloc(&d_und, bytes));
-            cudaError_t us = undistort_device(d_tmp, d_und, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream);
+            void* sc = nullptr;
+            int rcs = ensure_scratch(e, bytes, &sc);
+            if (rcs) return rcs;
+            uint8_t* d_und = (uint8_t*)sc;
+            cudaError_t us = undistort_device(d_tmp, d_und, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream, &e->d_undist_ir, &e->undist_ir_count);
             if (us == cudaSuccess) us = cudaMemcpyAsync(d_tmp, d_und, bytes, cudaMemcpyDeviceToDevice, e->stream);
-            if (us == cudaSuccess) us = cudaStreamSynchronize(e->stream);
-            cudaFree(d_und);
             if (us != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_set_masks: undistort failed: %s", cudaGetErrorString(us));
         }
         const long long n_rows = (long long)e->V * e->H, warps = n_rows * e->Ww;
@@ -465,7 +492,9 @@ static void inv3x3_lu(const double* A, double* inv) {
 }
 
 // device-to-device cv::undistort of n 8UC3 images on `stream`
-static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream) {
+// ir_buf / ir_count: optional grow-only device buffer for the per-stripe inverse matrices (an engine's); else allocated per call
+static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const double* K, const double* dist8, cudaStream_t stream,
+                                    double** ir_buf, size_t* ir_count) {
     int stripe = (1 << 12) / (W > 1 ? W : 1);
     if (stripe < 1) stripe = 1;
     if (stripe > H) stripe = H;
@@ -478,8 +507,16 @@ static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n,
         inv3x3_lu(Ar, &ir[(size_t)sidx * 9]);
     }
     double* d_ir = nullptr;
-    cudaError_t s = cudaMalloc(&d_ir, ir.size() * sizeof(double));
-    if (s != cudaSuccess) return s;
+    cudaError_t s = cudaSuccess;
+    if (ir_buf && *ir_count >= ir.size()) d_ir = *ir_buf;
+    else {
+        s = cudaMalloc(&d_ir, ir.size() * sizeof(double));
+        if (s != cudaSuccess) return s;
+        if (ir_buf) {  // the old buffer may still be read by a kernel on this stream
+            if (*ir_buf) { cudaStreamSynchronize(stream); cudaFree(*ir_buf); }
+            *ir_buf = d_ir; *ir_count = ir.size();
+        }
+    }
     s = cudaMemcpyAsync(d_ir, ir.data(), ir.size() * sizeof(double), cudaMemcpyHostToDevice, stream);
     if (s == cudaSuccess) s = cudaStreamSynchronize(stream);  // `ir` is a local
     if (s == cudaSuccess) {
@@ -491,7 +528,7 @@ static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n,
         s = cudaGetLastError();
         if (s == cudaSuccess) s = cudaStreamSynchronize(stream);
     }
-    cudaFree(d_ir);
+    if (!ir_buf) cudaFree(d_ir);
     return s;
 }
 
@@ -535,11 +572,12 @@ int vc_set_images_raw(vc_engine* e, const uint8_t* images_bgr) {
     if (bind_device(e)) return VC_ERR_CUDA;
     const size_t bytes = (size_t)e->V * e->H * e->W * 3;
     if (!e->d_images) VC_CUDA(e, cudaMalloc(&e->d_images, bytes));
-    uint8_t* d_raw = nullptr;
-    VC_CUDA(e, cudaMalloc(&d_raw, bytes));
+    void* sc = nullptr;
+    int rcs = ensure_scratch(e, bytes, &sc);
+    if (rcs) return rcs;
+    uint8_t* d_raw = (uint8_t*)sc;
     cudaError_t s = cudaMemcpyAsync(d_raw, images_bgr, bytes, cudaMemcpyHostToDevice, e->stream);
-    if (s == cudaSuccess) s = undistort_device(d_raw, e->d_images, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream);  // ColorReconstruction.h:23
-    cudaFree(d_raw);
+    if (s == cudaSuccess) s = undistort_device(d_raw, e->d_images, e->V, e->W, e->H, e->calib_K, e->calib_dist, e->stream, &e->d_undist_ir, &e->undist_ir_count);  // ColorReconstruction.h:23
     if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_set_images_raw: %s", cudaGetErrorString(s));
     return VC_OK;
 }
@@ -585,6 +623,7 @@ int vc_undistort_bgr(int32_t device, int32_t n, int32_t W, int32_t H, const uint
 int vc_reset(vc_engine* e) {
     if (!e) return VC_ERR_ARG;
     e->reset_pending = true;  // lazy: vc_carve(VC_EXACT) folds it into its coalesced fill pass
+    e->carved_implies_seen = true;
     e->gathered = false;
     e->have_colors = false;
     e->have_mc = false;
@@ -709,6 +748,19 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     if (count_executed) VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 8, 0, 4 * sizeof(unsigned long long), e->stream));
     if (mode == VC_EXACT) { rc = ensure_brick_buffers(e); if (rc) return rc; }
     if (mode != VC_EXACT) { rc = materialize_reset(e); if (rc) return rc; }
+    // Every kernel skips voxels that are already carved, which is exact as long as carved => seen.  An uploaded state may hold
+    // voxels that are carved but unseen; the reference still projects those and marks them seen (VoxelCarving.cpp:45-54).  They
+    // are carved as if occupied (so their `seen` bit comes out right; a carved voxel is seen by the view that carved it) and
+    // the uploaded occupancy is and-ed back afterwards.
+    uint32_t* d_saved_occ = nullptr;
+    if (!e->carved_implies_seen && !e->reset_pending) {
+        void* sc = nullptr;
+        rc = ensure_scratch(e, (size_t)e->slab_words * 4, &sc);
+        if (rc) return rc;
+        d_saved_occ = (uint32_t*)sc;
+        vc_unseen_begin_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), d_saved_occ, e->slab_words, e->Wx, e->g.X);
+        VC_CUDA(e, cudaGetLastError());
+    }
     set_mask_window(e, true);
     VC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     e->have_mid = mode == VC_EXACT;
@@ -721,6 +773,10 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
         if (rc) return rc;
+    }
+    if (d_saved_occ) {
+        vc_unseen_end_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), d_saved_occ, e->slab_words);
+        VC_CUDA(e, cudaGetLastError());
     }
     VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     rc = constants_used(e);
@@ -760,6 +816,10 @@ int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* 
     const int LZ = VC_BZ * VC_SUPER;
     int n_chunks = e->nz >= 8 * LZ ? 4 : (e->nz >= 2 * LZ ? 2 : 1);
     if (mode != VC_EXACT) n_chunks = 1;
+    // a cudaMemcpyAsync into pageable memory blocks the host until the chunk has arrived, so the next chunk's kernels would
+    // not be enqueued meanwhile: the chunked path only pays off with page-locked buffers (cudaHostAlloc / cudaHostRegister)
+    if (!host_pinned(occupied) || !host_pinned(seen)) n_chunks = 1;
+    if (!e->carved_implies_seen && !e->reset_pending) n_chunks = 1;  // uploaded state with carved-but-unseen voxels: vc_carve handles it
     if (n_chunks == 1) {  // nothing to overlap: plain sequence
         rc = vc_carve(e, mode, 0, -1, 0);
         if (!rc) rc = vc_download_occupied(e, occupied, n_words);
@@ -817,35 +877,38 @@ int vc_fast_carve(vc_engine* e, int32_t mode) {
     rc = vc_carve(e, mode, 0, -1, 0);
     if (rc) return rc;
     const long long n = e->slab_words;
-    uint32_t* F = nullptr;
-    int* d_changed = nullptr;
-    VC_CUDA(e, cudaMalloc(&F, n * 4 + 16));
-    d_changed = (int*)(F + n);
+    void* sc = nullptr;
+    rc = ensure_scratch(e, (size_t)n * 4 + 16, &sc);
+    if (rc) return rc;
+    uint32_t* F = (uint32_t*)sc;
+    int* d_changed = (int*)(F + n);
     VC_CUDA(e, cudaMemsetAsync(F, 0, n * 4 + 16, e->stream));
     uint32_t *occ = e->occ_slab(), *seen = e->seen_slab();
     const int X = e->g.X, Y = e->g.Y, Z = e->g.Z, Wx = e->Wx;
     vc_flood_seed_kernel<<<1, 1, 0, e->stream>>>(occ, F);
     const long long n_rows = (long long)Y * Z;
+    // a round = sweeps along x, y, z; the device-side "changed" flag is read back only every VC_FLOOD_POLL rounds (a round after
+    // convergence changes nothing, so at most VC_FLOOD_POLL - 1 rounds are wasted against a host round trip saved per round)
+    const int VC_FLOOD_POLL = 4;
     int rounds = 0;
-    for (;; rounds++) {
-        if (rounds > 100000) { cudaFree(F); return fail(e, VC_ERR_STATE, "vc_fast_carve: flood did not converge"); }
-        cudaMemsetAsync(d_changed, 0, sizeof(int), e->stream);
-        vc_flood_x_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, n_rows, X, d_changed);
-        // along y: one thread per (z, word column); along z: one thread per (y, word column)
-        vc_flood_axis_kernel<<<(unsigned)(((long long)Z * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Y, Wx, (long long)Y * Wx, Z, d_changed);
-        vc_flood_axis_kernel<<<(unsigned)(((long long)Y * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Z, (long long)Y * Wx, Wx, Y, d_changed);
+    for (;;) {
+        if (rounds > 100000) return fail(e, VC_ERR_STATE, "vc_fast_carve: flood did not converge");
+        VC_CUDA(e, cudaMemsetAsync(d_changed, 0, sizeof(int), e->stream));
+        for (int k = 0; k < VC_FLOOD_POLL; k++, rounds++) {
+            vc_flood_x_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, n_rows, X, d_changed);
+            // along y: one thread per (z, word column); along z: one thread per (y, word column)
+            vc_flood_axis_kernel<<<(unsigned)(((long long)Z * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Y, Wx, (long long)Y * Wx, Z, d_changed);
+            vc_flood_axis_kernel<<<(unsigned)(((long long)Y * Wx + 127) / 128), 128, 0, e->stream>>>(occ, F, Wx, X, Z, (long long)Y * Wx, Wx, Y, d_changed);
+        }
         int h = 0;
-        cudaError_t s = cudaMemcpyAsync(&h, d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-        if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
-        if (s != cudaSuccess) { cudaFree(F); return fail(e, VC_ERR_CUDA, "vc_fast_carve: %s", cudaGetErrorString(s)); }
+        VC_CUDA(e, cudaMemcpyAsync(&h, d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        VC_CUDA(e, cudaStreamSynchronize(e->stream));
         if (!h) break;
     }
     vc_flood_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(F, occ, seen, X, Y, Z, Wx);
-    cudaError_t s = cudaGetLastError();
-    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
-    cudaFree(F);
-    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_fast_carve: %s", cudaGetErrorString(s));
-    e->stats.flood_rounds = (uint64_t)rounds + 1;
+    VC_CUDA(e, cudaGetLastError());
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stats.flood_rounds = (uint64_t)rounds;
     return VC_OK;
 }
 
@@ -963,9 +1026,15 @@ int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* se
     e->reset_pending = false;  // overwritten entirely
     VC_CUDA(e, cudaMemcpyAsync(e->occ_slab(), occupied, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyAsync(e->seen_slab(), seen, n_words * 4, cudaMemcpyHostToDevice, e->stream));
-    vc_clear_padding_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), e->slab_words, e->Wx, e->g.X);
+    // padding cleared; [4] counts the words that hold a voxel which is carved but unseen (the reference would still mark such a
+    // voxel seen, VoxelCarving.cpp:54, so vc_carve must not skip it: see carve_unseen_begin)
+    VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 4, 0, sizeof(unsigned long long), e->stream));
+    vc_clear_padding_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), e->seen_slab(), e->slab_words, e->Wx, e->g.X, e->d_scalars + 4);
     VC_CUDA(e, cudaGetLastError());
+    unsigned long long n_bad = 0;
+    VC_CUDA(e, cudaMemcpyAsync(&n_bad, e->d_scalars + 4, sizeof n_bad, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->carved_implies_seen = n_bad == 0;
     e->gathered = false; e->have_colors = false; e->have_mc = false;
     return VC_OK;
 }
@@ -1234,6 +1303,20 @@ int vc_dense_from_volumes(vc_engine* e, int32_t apply_colors, int32_t handle_uns
     return VC_OK;
 }
 
+int vc_dense_apply_carved(vc_engine* e) {
+    if (!e) return VC_ERR_ARG;
+    int rc = dense_ready(e, "vc_dense_apply_carved", true);
+    if (rc) return rc;
+    rc = materialize_reset(e);
+    if (rc) return rc;
+    const size_t n = (size_t)e->g.X * e->g.Y * e->g.Z;
+    VcDense d{e->d_dense, e->g.X, e->g.Y, e->g.Z};
+    vc_dense_carved_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, e->occ_slab(), e->Wx);
+    VC_CUDA(e, cudaGetLastError());
+    e->have_mesh = false;
+    return VC_OK;
+}
+
 int vc_dense_closure(vc_engine* e, int32_t kernel_size) {
     if (!e) return VC_ERR_ARG;
     if (kernel_size < 1 || kernel_size % 2 != 1) return fail(e, VC_ERR_ARG, "Invalid kernel size for post processing, skipping...");  // Postprocessing3d.cpp:8-11
@@ -1267,32 +1350,32 @@ int vc_mc_mesh(vc_engine* e, float threshold, uint64_t* n_triangles) {
     const long long ncol = (long long)(e->g.X + 1) * (e->g.Y + 1);
     if (ncol > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "vc_mc_mesh: grid too large");
     const int nb = (int)((ncol + VC_SCAN_BLOCK - 1) / VC_SCAN_BLOCK);
-    uint32_t* d_counts = nullptr;
-    unsigned long long* d_sums = nullptr;
-    VC_CUDA(e, cudaMalloc(&d_counts, (size_t)ncol * 4));
-    VC_CUDA(e, cudaMalloc(&d_sums, ((size_t)nb + 1) * sizeof(unsigned long long)));
+    void* sc = nullptr;
+    const size_t counts_bytes = ((size_t)ncol * 4 + 15) / 16 * 16;
+    rc = ensure_scratch(e, counts_bytes + ((size_t)nb + 1) * sizeof(unsigned long long), &sc);
+    if (rc) return rc;
+    uint32_t* d_counts = (uint32_t*)sc;
+    unsigned long long* d_sums = (unsigned long long*)((char*)sc + counts_bytes);
     VcDense d{e->d_dense, e->g.X, e->g.Y, e->g.Z};
     vc_mc_count_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, e->stream>>>(d, threshold, d_counts);
     vc_scan_block_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(d_counts, d_counts, d_sums, ncol);
     vc_scan_sums_kernel<<<1, 1024, 0, e->stream>>>(d_sums, nb, d_sums + nb);
     vc_scan_add_kernel<<<nb, VC_SCAN_BLOCK, 0, e->stream>>>(d_counts, d_sums, ncol);
+    VC_CUDA(e, cudaGetLastError());
     unsigned long long total = 0;
-    cudaError_t s = cudaMemcpyAsync(&total, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, e->stream);
-    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
-    if (s == cudaSuccess && total > 0xffffffffull) { cudaFree(d_counts); cudaFree(d_sums); return fail(e, VC_ERR_CAPACITY, "vc_mc_mesh: %llu triangles exceed 32-bit offsets", total); }
-    if (s == cudaSuccess) {
-        cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb); e->d_mesh_verts = nullptr; e->d_mesh_rgb = nullptr;
-        if (total) {
-            s = cudaMalloc(&e->d_mesh_verts, total * 9 * sizeof(float));
-            if (s == cudaSuccess) s = cudaMalloc(&e->d_mesh_rgb, total * 3 * sizeof(uint32_t));
-            if (s == cudaSuccess) {
-                vc_mc_emit_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, e->stream>>>(d, threshold, d_counts, e->d_mesh_verts, e->d_mesh_rgb);
-                s = cudaStreamSynchronize(e->stream);
-            }
-        }
+    VC_CUDA(e, cudaMemcpyAsync(&total, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (total > 0xffffffffull) return fail(e, VC_ERR_CAPACITY, "vc_mc_mesh: %llu triangles exceed 32-bit offsets", total);
+    if (total > e->mesh_capacity) {  // triangle buffers are grow-only
+        cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb); e->d_mesh_verts = nullptr; e->d_mesh_rgb = nullptr; e->mesh_capacity = 0;
+        VC_CUDA(e, cudaMalloc(&e->d_mesh_verts, total * 9 * sizeof(float)));
+        VC_CUDA(e, cudaMalloc(&e->d_mesh_rgb, total * 3 * sizeof(uint32_t)));
+        e->mesh_capacity = total;
     }
-    cudaFree(d_counts); cudaFree(d_sums);
-    if (s != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_mc_mesh: %s", cudaGetErrorString(s));
+    if (total) {
+        vc_mc_emit_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, e->stream>>>(d, threshold, d_counts, e->d_mesh_verts, e->d_mesh_rgb);
+        VC_CUDA(e, cudaGetLastError());
+    }
     e->n_mesh_tris = total;
     e->have_mesh = true;
     *n_triangles = total;

@@ -38,6 +38,23 @@ def _host_ptr(a, dtype, nbytes_min, what):
     return addr, keep
 
 
+def _host_out_ptr(a, nbytes_min, what):
+    """OUTPUT buffer (numpy array or CPU torch tensor) -> address.  Never copies: the library writes through this pointer, so
+    the buffer must be 4-byte integer typed, C-contiguous and writeable as it stands."""
+    if hasattr(a, "data_ptr"):
+        addr, _ = _host_ptr(a, np.uint32, nbytes_min, what)
+        return addr
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{what}: output buffer must be a numpy array or a CPU torch tensor, got {type(a).__name__}")
+    if a.dtype not in (np.dtype(np.uint32), np.dtype(np.int32)):
+        raise ValueError(f"{what}: dtype {a.dtype}, expected uint32 (or int32)")
+    if not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+        raise ValueError(f"{what}: output buffer must be C-contiguous and writeable")
+    if a.nbytes < nbytes_min:
+        raise ValueError(f"{what}: buffer has {a.nbytes} bytes, needs {nbytes_min}")
+    return a.ctypes.data
+
+
 class VoxelEngine:
     """One engine = one GPU = one z-slab [z_begin, z_end) of an X*Y*Z grid."""
 
@@ -173,8 +190,8 @@ class VoxelEngine:
         n = (self.z_end - self.z_begin) * self.Y * self.Wx
         if out_occ is None:
             out_occ, out_seen = np.empty(self.slab_shape, np.uint32), np.empty(self.slab_shape, np.uint32)
-        a, ka = _host_ptr(out_occ, np.uint32, n * 4, "occupied buffer")
-        b, kb = _host_ptr(out_seen, np.uint32, n * 4, "seen buffer")
+        a = _host_out_ptr(out_occ, n * 4, "occupied buffer")
+        b = _host_out_ptr(out_seen, n * 4, "seen buffer")
         self._check(self._lib.vc_carve_download(self._h, mode, C.c_void_p(a), C.c_void_p(b), n))
         return out_occ, out_seen
 
@@ -228,7 +245,7 @@ class VoxelEngine:
             out = np.empty(self.slab_shape, np.uint32)
             addr = out.ctypes.data
         else:
-            addr, _ = _host_ptr(out, np.uint32, n * 4, "download buffer")
+            addr = _host_out_ptr(out, n * 4, "download buffer")
         self._check(fn(self._h, C.c_void_p(addr), n))
         return out
 
@@ -265,6 +282,10 @@ class VoxelEngine:
 
     def dense_from_volumes(self, apply_colors=False, handle_unseen=False):
         self._check(self._lib.vc_dense_from_volumes(self._h, int(bool(apply_colors)), int(bool(handle_unseen))))
+
+    def dense_apply_carved(self):
+        """model.set(x,y,z,0) for every carved voxel on the dense Model already on the device (VoxelCarving.cpp:52)"""
+        self._check(self._lib.vc_dense_apply_carved(self._h))
 
     def dense_closure(self, kernel_size=3):
         self._check(self._lib.vc_dense_closure(self._h, int(kernel_size)))

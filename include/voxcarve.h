@@ -8,7 +8,9 @@
  *
  * Conventions: plain pointers and sizes only; every function returns an int status
  * (VC_OK = 0); no exceptions cross the boundary; output buffers are caller-allocated;
- * an engine is not thread-safe (the reference is single-threaded, Benchmark.h:59-63);
+ * an engine is not thread-safe (the reference is single-threaded, Benchmark.h:59-63); engines on DIFFERENT devices may be driven
+ * from different threads, engines on the SAME device share its __constant__ view tables and must be driven from one thread at a
+ * time (the library orders their launches: a new owner of the tables waits for the previous owner's kernels);
  * all device memory is owned by the engine unless bound with vc_bind_volumes.
  * There is NO CPU fallback: without a CUDA device every call fails with VC_ERR_CUDA.
  *
@@ -136,6 +138,8 @@ VC_EXPORT int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t v
  * carved in z-chunks and every finished chunk is copied on a second stream while the next one is carving, so the
  * PCIe transfer overlaps the kernels.  Same result as vc_carve + vc_download_occupied + vc_download_seen. */
 VC_EXPORT int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* seen, uint64_t n_words);
+/* (the overlap needs PAGE-LOCKED buffers - cudaHostAlloc / cudaHostRegister: a copy into pageable memory blocks the host, so with
+ * pageable buffers the call degrades to the plain carve + two downloads.) */
 /* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): starts from the Model constructor state (it resets the
  * volumes itself) and needs the whole grid on this engine. */
 VC_EXPORT int vc_fast_carve(vc_engine* e, int32_t mode);
@@ -170,6 +174,8 @@ VC_EXPORT int vc_slab_words(const vc_engine* e, uint64_t* n_words); /* (z_end-z_
 /* Load this slab's volumes from HOST words: how the shim hands an existing Model (alpha != 0 and
  * Model::seen, e.g. after applyClosure, main.cpp:297-303) to vc_color / vc_mc_classify. Padding
  * bits are cleared. */
+/* A later vc_carve accumulates onto this state exactly like the reference: a voxel that arrives carved but unseen is still
+ * marked seen by every view that has it inside the image (VoxelCarving.cpp:45-54). */
 VC_EXPORT int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* seen, uint64_t n_words);
 VC_EXPORT int vc_download_occupied(vc_engine* e, uint32_t* words, uint64_t n_words);
 VC_EXPORT int vc_download_seen(vc_engine* e, uint32_t* words, uint64_t n_words);
@@ -191,6 +197,10 @@ VC_EXPORT int vc_dense_upload(vc_engine* e, const float* rgba);
  * apply_colors != 0: the records of the last vc_color (ColorReconstruction.cpp:41,66); handle_unseen != 0:
  * Model::handleUnseen (Model.cpp:36-47). */
 VC_EXPORT int vc_dense_from_volumes(vc_engine* e, int32_t apply_colors, int32_t handle_unseen);
+/* model.set(x, y, z, (0,0,0,0)) for every voxel the device volumes hold as carved (VoxelCarving.cpp:52), on the dense Model
+ * already on the device (vc_dense_upload): the Model after carve() when it held other state before (-intermediateMesh,
+ * VoxelCarving.cpp:65-68, takes a mesh of it after every view). */
+VC_EXPORT int vc_dense_apply_carved(vc_engine* e);
 /* applyClosure(model, kernelSize) (Postprocessing3d.h:10): returns VC_ERR_ARG for an even kernel size (reference: -1). */
 VC_EXPORT int vc_dense_closure(vc_engine* e, int32_t kernel_size);
 VC_EXPORT int vc_dense_download(vc_engine* e, float* rgba);

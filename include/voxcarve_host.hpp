@@ -107,6 +107,7 @@ class Engine {
     }
     // "next" rows: dense RGBA Model on the device
     void denseUpload(const std::vector<float>& rgba) { check(vc_dense_upload(h_, rgba.data())); }
+    void denseApplyCarved() { check(vc_dense_apply_carved(h_)); }
     void denseClosure(int kernelSize) { check(vc_dense_closure(h_, kernelSize)); }
     void denseDownload(std::vector<float>& rgba) { check(vc_dense_download(h_, rgba.data())); }
     uint64_t mcMesh(float threshold, std::vector<float>& verts, std::vector<uint32_t>& rgb) {
@@ -190,21 +191,47 @@ void colorPass(const ViewCache& views, ModelT& model, int mode) {
         model.set(x, y, z, Vec4Of<ModelT>((float)rgbn[i * 4], (float)rgbn[i * 4 + 1], (float)rgbn[i * 4 + 2], 1.f));
     }
 }
+
+// SimpleMesh::WriteMesh (MarchingCubes.h:59-87) for the triangle soup vc_mc_mesh leaves on the device: vertex = index coordinates
+// * (scale * voxel size) + translation (MarchingCubes.h:561-566), default ostream float formatting
+inline bool writeOff(const std::string& outFileName, uint64_t nt, const std::vector<float>& verts, const std::vector<uint32_t>& rgb,
+                     float sf, float tx, float ty, float tz) {
+    std::ofstream outFile(outFileName);
+    if (!outFile.is_open()) return false;
+    outFile << "OFF" << std::endl;
+    outFile << nt * 3 << " " << nt << " 0" << std::endl;
+    for (uint64_t i = 0; i < nt * 3; i++)
+        outFile << verts[i * 3] * sf + tx << " " << verts[i * 3 + 1] * sf + ty << " " << verts[i * 3 + 2] * sf + tz << std::endl;
+    for (uint64_t i = 0; i < nt; i++)
+        outFile << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << " " << rgb[i * 3] << " " << rgb[i * 3 + 1] << " " << rgb[i * 3 + 2] << std::endl;
+    outFile.close();
+    return true;
+}
 }  // namespace detail
 
-// carve() — VoxelCarving.cpp:60-72. With intermediateMeshes, `perView` (if given) receives the cube-index
-// summary after every view, where the reference writes out/intermediate/image_<i>_mesh.off (:65-68).
+// carve() — VoxelCarving.cpp:60-72.  With intermediateMeshes the Model's mesh after every view goes to
+// <intermediateDir>/image_<i>_mesh.off, translated by i * (X + 2) * size along x, exactly as :65-68 writes it (the directory
+// must exist: main.cpp:47 creates ./out/intermediate); `perView` (if given) also receives the cube-index summary per view.
 template <class ModelT>
-void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = false, std::vector<McSummary>* perView = nullptr) {
+void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = false, std::vector<McSummary>* perView = nullptr,
+           const std::string& intermediateDir = "out/intermediate") {
     std::cout << "LOG - VC: starting carving process (version 1)." << std::endl;
     Engine e(model.getX(), model.getY(), model.getZ(), model.getSize());
     e.setViews(views, false);
     std::vector<uint32_t> occ, seen;
     if (intermediateMeshes) {
+        e.denseUpload(detail::packVoxels(model));  // the Model as it is now (colours, earlier carves)
+        std::vector<float> verts;
+        std::vector<uint32_t> rgb;
         for (int i = 0; i < views.V; i++) {
             e.carve(VC_EXACT, i, i + 1);
-            const McSummary s = e.mcClassify();
-            if (perView) perView->push_back(s);
+            std::cout << "LOG - VC: generating intermediate mesh for image " << i << std::endl;
+            e.denseApplyCarved();
+            const uint64_t nt = e.mcMesh(0.5f, verts, rgb);
+            const float tx = (float)(i * (model.getX() + 2)) * model.getSize();  // Vector3f(i*(model.getX() + 2)*model.getSize(), 0, 0)
+            if (!detail::writeOff(intermediateDir + "/image_" + std::to_string(i) + "_mesh.off", nt, verts, rgb, 1.0f * model.getSize(), tx, 0.f, 0.f))
+                std::cout << "ERR - MC: unable to write output file!" << std::endl;  // the reference carries on (its bool result is ignored)
+            if (perView) perView->push_back(e.mcClassify());
         }
         occ = e.occupied();
         seen = e.seen();
@@ -292,18 +319,10 @@ bool marchingCubes(ModelT* model, float scale = 1.0f, const float* translation =
     std::cout << "LOG - MC: voxel processing completed.\n Writing mesh..." << std::endl;
     const float sf = scale * model->getSize();
     const float tx = translation ? translation[0] : 0.f, ty = translation ? translation[1] : 0.f, tz = translation ? translation[2] : 0.f;
-    std::ofstream outFile(outFileName);
-    if (!outFile.is_open()) {
+    if (!detail::writeOff(outFileName, nt, verts, rgb, sf, tx, ty, tz)) {
         std::cout << "ERR - MC: unable to write output file!" << std::endl;
         return false;
     }
-    outFile << "OFF" << std::endl;
-    outFile << nt * 3 << " " << nt << " 0" << std::endl;
-    for (uint64_t i = 0; i < nt * 3; i++)
-        outFile << verts[i * 3] * sf + tx << " " << verts[i * 3 + 1] * sf + ty << " " << verts[i * 3 + 2] * sf + tz << std::endl;
-    for (uint64_t i = 0; i < nt; i++)
-        outFile << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << " " << rgb[i * 3] << " " << rgb[i * 3 + 1] << " " << rgb[i * 3 + 2] << std::endl;
-    outFile.close();
     std::cout << "LOG - MC: Mesh written, marchingCubes completed." << std::endl;
     return true;
 }

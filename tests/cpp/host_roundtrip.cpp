@@ -1,7 +1,7 @@
 // Drives include/voxcarve_host.hpp the way main.cpp:248-303 drives the reference: a Model on the stack,
 // carve -> reconstructAvgColor -> handleUnseen -> cube-index pass.  MiniModel is a stand-in with the
 // interface of the reference Model (Model.h:93-163) so this builds without OpenCV/Eigen.
-// usage: host_roundtrip <case.bin> <out.bin>
+// usage: host_roundtrip <case.bin> <out.bin> [<mesh.off> [<intermediate dir>]]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     try {
         MiniModel model(X, Y, Z, s);
         std::vector<vc::McSummary> perView;
-        vc::carve(views, model, /*intermediateMeshes=*/true, &perView);
+        vc::carve(views, model, /*intermediateMeshes=*/true, &perView, argc > 4 ? argv[4] : "out/intermediate");
         vc::reconstructAvgColor(views, model);
         model.handleUnseen();
         const vc::McSummary mc = vc::marchingCubesClassify(model);

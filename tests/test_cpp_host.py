@@ -53,7 +53,9 @@ def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
         vs.images_bgr.astype(np.uint8).tofile(f)
     out = tmp_path / "out.bin"
     off = tmp_path / "mesh.off"
-    subprocess.check_call([_build(tmp_path, lib_built), str(case), str(out), str(off)], stdout=subprocess.DEVNULL)
+    inter = tmp_path / "intermediate"
+    inter.mkdir()
+    subprocess.check_call([_build(tmp_path, lib_built), str(case), str(out), str(off), str(inter)], stdout=subprocess.DEVNULL)
     raw = open(out, "rb").read()
     n = X * Y * Z
     vox = np.frombuffer(raw, np.float32, n * 4).reshape(n, 4)
@@ -75,6 +77,17 @@ def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
     rh, _, rnt = oracle.mc_classify(X, Y, Z, ro)
     assert np.array_equal(hist, rh) and ntris == rnt
     assert nv == vs.V and per_view[-1] == rnt  # -intermediateMesh: the last per-view summary is the final one
+    # -intermediateMesh (VoxelCarving.cpp:65-68): after view i, marchingCubes(&model, 1.0f, (i*(X+2)*size, 0, 0), 0.5f,
+    # "out/intermediate/image_<i>_mesh.off") of the Model carved by views 0..i - text-identical to the oracle's
+    acc = np.full_like(ro, 0xffffffff)
+    for i in range(vs.V):
+        oi, _ = oracle.carve(X, Y, Z, s, vs.P[i:i + 1], vs.W, vs.H, mask_bits=vs.mask_bits[i:i + 1])
+        acc &= oi
+        mv, mc = oracle.marching_cubes(X, Y, Z, oracle.dense_model(X, Y, Z, acc), 0.5)
+        assert len(mv) == per_view[i]
+        ref_i = tmp_path / f"ref_{i}.off"
+        oracle.write_off(str(ref_i), mv, mc, np.float32(1.0) * s, (np.float32(i * (X + 2)) * s, 0.0, 0.0))
+        assert open(inter / f"image_{i}_mesh.off").read() == open(ref_i).read(), i
     # applyClosure(&model, 3) + marchingCubes(&model, 1.5, (0.5,-0.25,2), 0.5, file): the .off text equals the oracle's
     dense = exp.copy()
     full = np.concatenate([dense, (vox[:, 3:4] != 0).astype(np.float32)], axis=1)

@@ -719,3 +719,58 @@ def test_hierarchical_carve_random_stress(A, oracle, seed):
             e.carve(0, 0, cut)
             e.carve(0, cut, -1)
             assert np.array_equal(e.download_occupied(), ro) and np.array_equal(e.download_seen(), rs)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_carve_accumulates_onto_uploaded_state_like_the_reference(A, oracle, mode):
+    """vc_upload_volumes + vc_carve = carve() called on a Model that already holds state.  The reference projects EVERY voxel,
+    occupied or not, and marks it seen when its pixel is inside the image (VoxelCarving.cpp:45-54): a voxel that arrives carved but
+    unseen must come out seen if any view has it inside, although every kernel skips already-carved voxels."""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 70, 37, 29
+    w = Workload(70, 9, 200, 150, seed=3, dims=(X, Y, Z))
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    rng = np.random.default_rng(7)
+    Wx = (X + 31) // 32
+    valid = np.full(Wx, 0xffffffff, np.uint32)
+    valid[-1] = (1 << (X - 32 * (Wx - 1))) - 1 if X % 32 else 0xffffffff
+    occ0 = rng.integers(0, 2 ** 32, size=(Z, Y, Wx), dtype=np.uint64).astype(np.uint32) & valid
+    seen0 = rng.integers(0, 2 ** 32, size=(Z, Y, Wx), dtype=np.uint64).astype(np.uint32) & valid
+    occ0[: Z // 3] = 0          # a block that is carved and unseen as a whole (whole bricks of it)
+    seen0[: Z // 3] = 0
+    assert ((~occ0) & (~seen0) & valid).any()
+    with A.VoxelEngine(X, Y, Z, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        e.upload_volumes(occ0, seen0)
+        e.carve(mode)
+        occ, seen = e.download_occupied(), e.download_seen()
+        assert np.array_equal(occ, occ0 & ro), "occupied: uploaded state AND what the views carve"
+        assert np.array_equal(seen, seen0 | rs), "seen: uploaded state OR every voxel some view has inside its image"
+        e.upload_volumes(occ0, seen0)
+        o2, s2 = e.carve_download(mode=mode)
+        assert np.array_equal(o2, occ) and np.array_equal(s2, seen)
+
+
+def test_engines_sharing_a_device_keep_their_own_views(A, oracle):
+    """the view tables live in per-device __constant__ memory shared by every engine on the GPU: two engines with DIFFERENT
+    views, driven alternately without synchronising in between, must each carve with their own"""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 96, 64, 48
+    wa = Workload(96, 12, 320, 240, seed=1, dims=(X, Y, Z))
+    wb = Workload(96, 5, 256, 200, seed=2, dims=(X, Y, Z))
+    ra = oracle.carve(X, Y, Z, wa.s, wa.P, wa.W, wa.H, mask_bits=wa.mask_bits)
+    rb = oracle.carve(X, Y, Z, wb.s, wb.P, wb.W, wb.H, mask_bits=wb.mask_bits)
+    with A.VoxelEngine(X, Y, Z, wa.s) as ea, A.VoxelEngine(X, Y, Z, wb.s) as eb:
+        ea.set_views(wa.P, wa.W, wa.H, wa.M), ea.set_masks_bits(wa.mask_bits), ea.set_images(wa.images_bgr())
+        eb.set_views(wb.P, wb.W, wb.H, wb.M), eb.set_masks_bits(wb.mask_bits), eb.set_images(wb.images_bgr())
+        for _ in range(6):   # launches of one engine still in flight when the other uploads its tables
+            ea.reset(), ea.carve(2)
+            eb.reset(), eb.carve(2)
+            ea.reset(), ea.carve(0), ea.color(2)
+            eb.reset(), eb.carve(0), eb.color(1)
+        for e, r, w, mode in ((ea, ra, wa, 2), (eb, rb, wb, 1)):
+            assert np.array_equal(e.download_occupied(), r[0]) and np.array_equal(e.download_seen(), r[1])
+            idx, rgbn = e.download_colors()
+            ridx, rrgbn = oracle.color(X, Y, Z, w.s, w.P, w.M, w.W, w.H, w.images_bgr(), r[0], mode)
+            assert np.array_equal(idx, ridx) and np.array_equal(rgbn, rrgbn)

@@ -116,3 +116,22 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_output_buffers_are_never_copied_behind_the_callers_back():
+    """engine._host_out_ptr: an output buffer must be usable as it stands (4-byte integers, C-contiguous, writeable); anything
+    else raises instead of letting the library write into a temporary copy"""
+    from ar_voxel_project_b200.engine import _host_out_ptr
+    ok = np.zeros((4, 3, 2), np.uint32)
+    assert _host_out_ptr(ok, ok.nbytes, "t") == ok.ctypes.data
+    assert _host_out_ptr(ok.view(np.int32), ok.nbytes, "t") == ok.ctypes.data
+    for bad in (np.zeros((4, 3, 2), np.int64), np.zeros((4, 3, 2), np.float32), np.zeros((4, 3, 4), np.uint32)[:, :, ::2],
+                np.zeros((2, 3, 2), np.uint32)):
+        with pytest.raises(ValueError):
+            _host_out_ptr(bad, ok.nbytes, "t")
+    ro = np.zeros((4, 3, 2), np.uint32)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        _host_out_ptr(ro, ok.nbytes, "t")
+    with pytest.raises(TypeError):
+        _host_out_ptr([0] * 24, ok.nbytes, "t")
