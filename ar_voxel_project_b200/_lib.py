@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvoxcarve.so")
 
-VC_OK, VC_ERR_ARG, VC_ERR_CUDA, VC_ERR_STATE, VC_ERR_CAPACITY = 0, 1, 2, 3, 4
+VC_OK, VC_ERR_ARG, VC_ERR_CUDA, VC_ERR_STATE, VC_ERR_CAPACITY, VC_ERR_COMM = 0, 1, 2, 3, 4, 5
 VC_EXACT, VC_FAST_F32, VC_EXACT_FLAT = 0, 1, 2
 VC_COLOR_CLOSEST, VC_COLOR_AVG = 1, 2
 VC_MASK_BITS, VC_MASK_BGR8, VC_MASK_BGR8_RAW = 0, 1, 2
@@ -56,6 +56,19 @@ SIGNATURES = {
     "vc_bind_volumes": (C.c_int, [_P, _P, _P]),
     "vc_device_volumes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "vc_set_gathered": (C.c_int, [_P, C.c_int32]),
+    "vc_alloc_full_volumes": (C.c_int, [_P]),
+    "vc_halo_words": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "vc_export_halo": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "vc_import_halo": (C.c_int, [_P, C.c_int32, _P]),
+    "vc_exchange_halos_peer": (C.c_int, [C.POINTER(_P), C.c_int32]),
+    "vc_comm_unique_id": (C.c_int, [_P]),
+    "vc_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vc_comm_destroy": (C.c_int, [_P]),
+    "vc_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vc_exchange_halos": (C.c_int, [_P]),
+    "vc_gather": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "vc_comm_allreduce_u64": (C.c_int, [_P, _P, C.c_int32]),
+    "vc_download_full": (C.c_int, [_P, C.c_int32, _P, C.c_uint64]),
     "vc_slab_words": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "vc_upload_volumes": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "vc_download_occupied": (C.c_int, [_P, _P, C.c_uint64]),

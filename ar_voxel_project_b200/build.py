@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--ftz=false", "--prec-div=true", "--prec-sqrt=true",  # IEEE f32 divide/sqrt, denormals kept (reference is x86 SSE)
     "-Xptxas", "-v",
+    "-ldl",  # NCCL is dlopen-ed by vc_comm_init (no load-time dependency); nvtx3 is header-only and dlopen-s its injection library
 ]
 
 

@@ -4,7 +4,11 @@
 #include "../../include/voxcarve.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>             // types and prototypes only: the library is dlopen-ed by vc_comm_init (see load_nccl)
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges named after the reference's Benchmark phases (Benchmark.h:86-124)
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -45,8 +49,17 @@ struct vc_engine {
     bool have_mid = false;
     // volumes
     uint32_t *d_occ_own = nullptr, *d_seen_own = nullptr;    // slab-sized, engine-owned
-    uint32_t *d_occ_full = nullptr, *d_seen_full = nullptr;  // caller-owned whole grid (vc_bind_volumes)
+    uint32_t *d_occ_full = nullptr, *d_seen_full = nullptr;  // whole grid: caller-owned (vc_bind_volumes) or the two below
+    uint32_t *d_occ_full_own = nullptr, *d_seen_full_own = nullptr;  // vc_alloc_full_volumes
     bool gathered = false;
+    // Halo planes of `occupied`: z_begin - 1 and z_end sit right next to the slab - inside the whole-grid buffer when one is
+    // bound, in the two extra planes of d_occ_own otherwise - so the consumers address them like any other plane.
+    bool halo_lo = false, halo_hi = false;   // valid (imported since the neighbour slab was last carved)
+    cudaEvent_t ev_halo = nullptr;           // "my slab is complete" for vc_exchange_halos_peer
+    ncclComm_t comm = nullptr;               // vc_comm_init
+    int comm_rank = 0, comm_world = 1;
+    unsigned long long* d_reduce = nullptr;  // staging of vc_comm_allreduce_u64
+    size_t reduce_cap = 0;
     // views
     int V = 0, W = 0, H = 0, Ww = 0;
     unsigned long long views_version = 0;
@@ -96,7 +109,7 @@ struct vc_engine {
     vc_stats stats{};
     std::string err;
 
-    uint32_t* occ_slab() const { return d_occ_full ? d_occ_full + (long long)g.z_begin * plane_words : d_occ_own; }
+    uint32_t* occ_slab() const { return d_occ_full ? d_occ_full + (long long)g.z_begin * plane_words : d_occ_own + plane_words; }  // own: one halo plane in front
     uint32_t* seen_slab() const { return d_seen_full ? d_seen_full + (long long)g.z_begin * plane_words : d_seen_own; }
     bool whole_grid() const { return g.z_begin == 0 && g.z_end == g.Z; }
 };
@@ -178,7 +191,10 @@ VcVolView vol_view(const vc_engine* e) {
     VcVolView g;
     g.X = e->g.X; g.Y = e->g.Y; g.Z = e->g.Z; g.Wx = e->Wx;
     if (e->d_occ_full && e->gathered) { g.base = e->d_occ_full; g.cz0 = 0; g.cz1 = e->g.Z; }
-    else { g.base = e->occ_slab(); g.cz0 = e->g.z_begin; g.cz1 = e->g.z_end; }
+    else {
+        const int lo = (e->halo_lo && e->g.z_begin > 0) ? 1 : 0, hi = (e->halo_hi && e->g.z_end < e->g.Z) ? 1 : 0;
+        g.base = e->occ_slab() - (long long)lo * e->plane_words; g.cz0 = e->g.z_begin - lo; g.cz1 = e->g.z_end + hi;
+    }
     return g;
 }
 
@@ -339,7 +355,9 @@ void vc_destroy(vc_engine* e) {
     cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
-    cudaFree(e->d_scratch); cudaFree(e->d_undist_ir);
+    cudaFree(e->d_scratch); cudaFree(e->d_undist_ir); cudaFree(e->d_occ_full_own); cudaFree(e->d_seen_full_own); cudaFree(e->d_reduce);
+    if (e->comm) vc_comm_destroy(e);
+    if (e->ev_halo) cudaEventDestroy(e->ev_halo);
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -536,7 +554,7 @@ static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n,
 static int ensure_volumes(vc_engine* e) {
     if (e->d_occ_full || e->d_occ_own) return VC_OK;
     if (bind_device(e)) return VC_ERR_CUDA;
-    VC_CUDA(e, cudaMalloc(&e->d_occ_own, e->slab_words * 4));
+    VC_CUDA(e, cudaMalloc(&e->d_occ_own, (e->slab_words + 2 * e->plane_words) * 4));  // + the halo planes z_begin - 1 and z_end
     VC_CUDA(e, cudaMalloc(&e->d_seen_own, e->slab_words * 4));
     return VC_OK;
 }
@@ -625,6 +643,7 @@ int vc_reset(vc_engine* e) {
     e->reset_pending = true;  // lazy: vc_carve(VC_EXACT) folds it into its coalesced fill pass
     e->carved_implies_seen = true;
     e->gathered = false;
+    e->halo_lo = e->halo_hi = false;
     e->have_colors = false;
     e->have_mc = false;
     return VC_OK;
@@ -738,8 +757,16 @@ static int carve_check(vc_engine* e, const char* who, int32_t mode, int32_t& vie
     return ensure_constants(e);
 }
 
+// NVTX range named after a phase of the reference's Benchmark singleton (Benchmark.h:86-124): Carving, Coloring,
+// PostProcessing, MarchingCubes - what a profiler timeline of a -c=5 / -c=6 run shows next to the reference's own phases
+struct PhaseRange {
+    explicit PhaseRange(const char* name) { nvtxRangePushA(name); }
+    ~PhaseRange() { nvtxRangePop(); }
+};
+
 int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, int32_t count_executed) {
     if (!e) return VC_ERR_ARG;
+    PhaseRange nvtx("Carving");
     int rc = carve_check(e, "vc_carve", mode, view_begin, view_end);
     if (rc) return rc;
     VcCarveParams p = carve_params(e, view_begin, view_end);
@@ -801,6 +828,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
         if (mode == VC_EXACT) { e->stats.filter_rows = fl[0]; e->stats.filter_slow_rows = fl[1]; e->stats.filter_mismatches = fl[2]; e->stats.subbrick_corner_views = fl[3]; }
     }
     e->gathered = false;
+    e->halo_lo = e->halo_hi = false;  // the neighbours carve too: their planes are stale
     e->have_colors = false;
     e->have_mc = false;
     return VC_OK;
@@ -809,6 +837,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
 int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* seen, uint64_t n_words) {
     if (!e) return VC_ERR_ARG;
     if (!occupied || !seen) return fail(e, VC_ERR_ARG, "vc_carve_download: null buffer");
+    PhaseRange nvtx("Carving");
     if (n_words < (uint64_t)e->slab_words) return fail(e, VC_ERR_CAPACITY, "vc_carve_download: buffers hold %llu words, slab has %lld", (unsigned long long)n_words, e->slab_words);
     int32_t v0 = 0, v1 = -1;
     int rc = carve_check(e, "vc_carve_download", mode, v0, v1);
@@ -861,6 +890,7 @@ int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* 
     e->stats.brick_corner_views = 0;
     e->stats.last_carve_ms = -1.0;
     e->gathered = false;
+    e->halo_lo = e->halo_hi = false;
     e->have_colors = false;
     e->have_mc = false;
     VC_CUDA(e, cudaStreamSynchronize(e->copy_stream));
@@ -870,6 +900,7 @@ int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* 
 
 int vc_fast_carve(vc_engine* e, int32_t mode) {
     if (!e) return VC_ERR_ARG;
+    PhaseRange nvtx("Carving");
     if (!e->whole_grid()) return fail(e, VC_ERR_STATE, "vc_fast_carve: the flood from voxel (0,0,0) needs the whole grid on one engine (slab [%d,%d) of Z=%d)", e->g.z_begin, e->g.z_end, e->g.Z);
     // the set carve() would carve, on a fresh Model (fastCarve starts from the constructor state, main.cpp:248-264)
     int rc = vc_reset(e);
@@ -989,6 +1020,10 @@ int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full) {
     if (!d_occupied_full != !d_seen_full) return fail(e, VC_ERR_ARG, "vc_bind_volumes: bind both volumes or neither");
     if (bind_device(e)) return VC_ERR_CUDA;
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->d_occ_full_own && d_occupied_full != e->d_occ_full_own) {  // replaces engine-owned whole-grid buffers
+        cudaFree(e->d_occ_full_own); cudaFree(e->d_seen_full_own);
+        e->d_occ_full_own = e->d_seen_full_own = nullptr;
+    }
     e->d_occ_full = (uint32_t*)d_occupied_full;
     e->d_seen_full = (uint32_t*)d_seen_full;
     e->gathered = false;
@@ -1035,7 +1070,7 @@ int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* se
     VC_CUDA(e, cudaMemcpyAsync(&n_bad, e->d_scalars + 4, sizeof n_bad, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     e->carved_implies_seen = n_bad == 0;
-    e->gathered = false; e->have_colors = false; e->have_mc = false;
+    e->gathered = false; e->halo_lo = e->halo_hi = false; e->have_colors = false; e->have_mc = false;
     return VC_OK;
 }
 
@@ -1069,12 +1104,15 @@ int vc_count_occupied(vc_engine* e, uint64_t* n_occupied, uint64_t* n_seen) {
 // neighbour planes z_begin-1 and z_end must be addressable unless they lie outside the grid
 static int need_halo(vc_engine* e, const char* who) {
     if (e->whole_grid() || (e->d_occ_full && e->gathered)) return VC_OK;
-    return fail(e, VC_ERR_STATE, "%s: slab [%d,%d) of Z=%d needs its neighbour planes: bind a full volume, all-gather, vc_set_gathered(1)",
+    if ((e->g.z_begin == 0 || e->halo_lo) && (e->g.z_end == e->g.Z || e->halo_hi)) return VC_OK;
+    return fail(e, VC_ERR_STATE, "%s: slab [%d,%d) of Z=%d needs its neighbour planes: exchange the one-plane halos (vc_exchange_halos / "
+                "vc_exchange_halos_peer / vc_import_halo), or gather the whole grid (vc_gather, or an external all-gather + vc_set_gathered(1))",
                 who, e->g.z_begin, e->g.z_end, e->g.Z);
 }
 
 int vc_color(vc_engine* e, int32_t color_mode) {
     if (!e) return VC_ERR_ARG;
+    PhaseRange nvtx("Coloring");
     if (color_mode != VC_COLOR_CLOSEST && color_mode != VC_COLOR_AVG) return fail(e, VC_ERR_ARG, "vc_color: mode must be 1 (closest) or 2 (average), got %d", color_mode);
     if (e->V == 0 || !e->d_images) return fail(e, VC_ERR_STATE, "vc_color: views and images must be set first");
     if (!e->have_M) return fail(e, VC_ERR_STATE, "vc_color: vc_set_views was given M = NULL (camera translations are needed for the depth)");
@@ -1152,6 +1190,7 @@ int vc_download_colors(vc_engine* e, uint64_t* idx, uint8_t* rgbn, uint64_t capa
 
 int vc_mc_classify(vc_engine* e) {
     if (!e) return VC_ERR_ARG;
+    PhaseRange nvtx("MarchingCubes");
     int rc = need_halo(e, "vc_mc_classify");
     if (rc) return rc;
     if (bind_device(e)) return VC_ERR_CUDA;
@@ -1319,6 +1358,7 @@ int vc_dense_apply_carved(vc_engine* e) {
 
 int vc_dense_closure(vc_engine* e, int32_t kernel_size) {
     if (!e) return VC_ERR_ARG;
+    PhaseRange nvtx("PostProcessing");
     if (kernel_size < 1 || kernel_size % 2 != 1) return fail(e, VC_ERR_ARG, "Invalid kernel size for post processing, skipping...");  // Postprocessing3d.cpp:8-11
     int rc = dense_ready(e, "vc_dense_closure", true);
     if (rc) return rc;
@@ -1345,6 +1385,7 @@ int vc_dense_download(vc_engine* e, float* rgba) {
 
 int vc_mc_mesh(vc_engine* e, float threshold, uint64_t* n_triangles) {
     if (!e || !n_triangles) return VC_ERR_ARG;
+    PhaseRange nvtx("MarchingCubes");
     int rc = dense_ready(e, "vc_mc_mesh", true);
     if (rc) return rc;
     const long long ncol = (long long)(e->g.X + 1) * (e->g.Y + 1);
@@ -1408,6 +1449,298 @@ int vc_selftest(int32_t device, int32_t which, uint64_t n, uint64_t seed, uint64
     if (s != cudaSuccess) return fail(nullptr, VC_ERR_CUDA, "vc_selftest: %s", cudaGetErrorString(s));
     *mismatches = h[0];
     *checked = h[1];
+    return VC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: one-plane halos and collectives.  Voxels are independent, so carving needs no exchange; the
+// consumers of the grid read one neighbour plane of `occupied` (isInner, Model.h:126-132: z - 1 and z + 1; the cube index,
+// MarchingCubes.h:537-552: z + 1).  Engines in one process swap those planes with plain device copies
+// (vc_exchange_halos_peer); engines in different processes - one rank per GPU - through NCCL send/recv (vc_exchange_halos);
+// vc_gather assembles the whole grid, which only a host-side Model needs.
+// NCCL is loaded at run time (dlopen), so libvoxcarve.so has no load-time dependency on it: a process that already
+// carries an NCCL (PyTorch ships its own) shares that copy, everything else picks up the system's libnccl.so.2.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int version = 0;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    std::string error;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+const NcclApi* load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mutex);
+    if (g_nccl.handle) return &g_nccl;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy this process already carries (e.g. PyTorch's), if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { g_nccl.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+    NcclApi a;
+    a.handle = h;
+#define VC_NCCL_SYM(field, name)                                                                     \
+    a.field = (decltype(a.field))dlsym(h, name);                                                     \
+    if (!a.field) { g_nccl.error = std::string("libnccl.so.2 lacks ") + name; dlclose(h); return nullptr; }
+    VC_NCCL_SYM(GetVersion, "ncclGetVersion") VC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") VC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    VC_NCCL_SYM(CommDestroy, "ncclCommDestroy") VC_NCCL_SYM(GetErrorString, "ncclGetErrorString") VC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    VC_NCCL_SYM(GroupEnd, "ncclGroupEnd") VC_NCCL_SYM(Send, "ncclSend") VC_NCCL_SYM(Recv, "ncclRecv")
+    VC_NCCL_SYM(AllGather, "ncclAllGather") VC_NCCL_SYM(AllReduce, "ncclAllReduce")
+#undef VC_NCCL_SYM
+    a.GetVersion(&a.version);
+    g_nccl = a;
+    return &g_nccl;
+}
+
+#define VC_NCCL(e, api, call)                                                                                            \
+    do {                                                                                                                 \
+        ncclResult_t _r = (call);                                                                                        \
+        if (_r != ncclSuccess)                                                                                           \
+            return fail((e), VC_ERR_COMM, "%s failed: %s (%s:%d)", #call, (api)->GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+// first plane of the halo slot `which` (0: plane z_begin - 1, 1: plane z_end), or null when that plane is outside the grid
+uint32_t* halo_slot(vc_engine* e, int which) {
+    if (which == 0) return e->g.z_begin > 0 ? e->occ_slab() - e->plane_words : nullptr;
+    return e->g.z_end < e->g.Z ? e->occ_slab() + e->slab_words : nullptr;
+}
+}  // namespace
+
+extern "C" {
+
+int vc_alloc_full_volumes(vc_engine* e) {
+    if (!e) return VC_ERR_ARG;
+    if (bind_device(e)) return VC_ERR_CUDA;
+    if (e->d_occ_full_own) return VC_OK;
+    const size_t bytes = (size_t)e->g.Z * e->plane_words * 4;
+    uint32_t *o = nullptr, *s = nullptr;
+    VC_CUDA(e, cudaMalloc(&o, bytes));
+    if (cudaMalloc(&s, bytes) != cudaSuccess) { cudaFree(o); cudaGetLastError(); return fail(e, VC_ERR_CUDA, "vc_alloc_full_volumes: out of device memory (%zu bytes per volume)", bytes); }
+    int rc = vc_bind_volumes(e, o, s);  // drops the slab-sized volumes' role; resets the state
+    if (rc) { cudaFree(o); cudaFree(s); return rc; }
+    e->d_occ_full_own = o;
+    e->d_seen_full_own = s;
+    cudaFree(e->d_occ_own); cudaFree(e->d_seen_own);
+    e->d_occ_own = e->d_seen_own = nullptr;
+    return VC_OK;
+}
+
+int vc_halo_words(const vc_engine* e, uint64_t* n_words) {
+    if (!e || !n_words) return VC_ERR_ARG;
+    *n_words = (uint64_t)e->plane_words;
+    return VC_OK;
+}
+
+int vc_export_halo(vc_engine* e, int32_t which, void** d_plane) {
+    if (!e || !d_plane || (which != 0 && which != 1)) return VC_ERR_ARG;
+    int rc = materialize_reset(e);
+    if (rc) return rc;
+    *d_plane = which == 0 ? e->occ_slab() : e->occ_slab() + e->slab_words - e->plane_words;
+    return VC_OK;
+}
+
+int vc_import_halo(vc_engine* e, int32_t which, const void* d_plane) {
+    if (!e || (which != 0 && which != 1)) return VC_ERR_ARG;
+    if (bind_device(e)) return VC_ERR_CUDA;
+    bool& valid = which == 0 ? e->halo_lo : e->halo_hi;
+    if (!d_plane) { valid = false; return VC_OK; }
+    int rc = ensure_volumes(e);
+    if (rc) return rc;
+    uint32_t* dst = halo_slot(e, which);
+    if (!dst) return fail(e, VC_ERR_ARG, "vc_import_halo: plane %s of slab [%d,%d) lies outside the grid (it is empty by definition, Model.h:119-124)",
+                          which == 0 ? "z_begin - 1" : "z_end", e->g.z_begin, e->g.z_end);
+    VC_CUDA(e, cudaMemcpyAsync(dst, d_plane, (size_t)e->plane_words * 4, cudaMemcpyDefault, e->stream));
+    valid = true;
+    e->have_colors = false;
+    e->have_mc = false;
+    return VC_OK;
+}
+
+int vc_exchange_halos_peer(vc_engine** engines, int32_t n) {
+    if (!engines || n < 1) return VC_ERR_ARG;
+    std::vector<vc_engine*> es(engines, engines + n);
+    for (vc_engine* e : es) if (!e) return VC_ERR_ARG;
+    std::sort(es.begin(), es.end(), [](const vc_engine* a, const vc_engine* b) { return a->g.z_begin < b->g.z_begin; });
+    vc_engine* e0 = es[0];
+    for (int i = 0; i < n; i++) {
+        vc_engine* e = es[i];
+        if (e->g.X != e0->g.X || e->g.Y != e0->g.Y || e->g.Z != e0->g.Z) return fail(e, VC_ERR_ARG, "vc_exchange_halos_peer: engines of different grids");
+        if (i + 1 < n && e->g.z_end != es[i + 1]->g.z_begin)
+            return fail(e, VC_ERR_ARG, "vc_exchange_halos_peer: slabs [%d,%d) and [%d,%d) are not adjacent", e->g.z_begin, e->g.z_end, es[i + 1]->g.z_begin, es[i + 1]->g.z_end);
+        if (bind_device(e)) return VC_ERR_CUDA;
+        int rc = materialize_reset(e);
+        if (rc) return rc;
+        if (!e->ev_halo) VC_CUDA(e, cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming));
+        VC_CUDA(e, cudaEventRecord(e->ev_halo, e->stream));  // my slab is complete here
+    }
+    const size_t bytes = (size_t)e0->plane_words * 4;
+    for (int i = 0; i + 1 < n; i++) {
+        vc_engine *a = es[i], *b = es[i + 1];  // a below b: a's last plane is b's z_begin - 1, b's first plane is a's z_end
+        if (bind_device(b)) return VC_ERR_CUDA;
+        VC_CUDA(b, cudaStreamWaitEvent(b->stream, a->ev_halo, 0));
+        VC_CUDA(b, cudaMemcpyAsync(halo_slot(b, 0), a->occ_slab() + a->slab_words - a->plane_words, bytes, cudaMemcpyDefault, b->stream));
+        b->halo_lo = true; b->have_colors = false; b->have_mc = false;
+        if (bind_device(a)) return VC_ERR_CUDA;
+        VC_CUDA(a, cudaStreamWaitEvent(a->stream, b->ev_halo, 0));
+        VC_CUDA(a, cudaMemcpyAsync(halo_slot(a, 1), b->occ_slab(), bytes, cudaMemcpyDefault, a->stream));
+        a->halo_hi = true; a->have_colors = false; a->have_mc = false;
+    }
+    return VC_OK;
+}
+
+int vc_comm_unique_id(void* unique_id_128) {
+    if (!unique_id_128) return VC_ERR_ARG;
+    const NcclApi* api = load_nccl();
+    if (!api) return fail(nullptr, VC_ERR_COMM, "vc_comm_unique_id: %s", g_nccl.error.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, VC_ERR_COMM, "ncclGetUniqueId failed: %s", api->GetErrorString(r));
+    memcpy(unique_id_128, &id, sizeof id);
+    return VC_OK;
+}
+
+int vc_comm_init(vc_engine* e, int32_t rank, int32_t world, const void* unique_id_128) {
+    if (!e) return VC_ERR_ARG;
+    if (!unique_id_128 || world < 1 || rank < 0 || rank >= world) return fail(e, VC_ERR_ARG, "vc_comm_init: bad rank %d / world %d / id", rank, world);
+    if (e->comm) return fail(e, VC_ERR_STATE, "vc_comm_init: communicator already initialised (vc_comm_destroy first)");
+    const NcclApi* api = load_nccl();
+    if (!api) return fail(e, VC_ERR_COMM, "vc_comm_init: %s", g_nccl.error.c_str());
+    if (bind_device(e)) return VC_ERR_CUDA;
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof id);
+    VC_NCCL(e, api, api->CommInitRank(&e->comm, world, id, rank));  // blocks until every rank has called it
+    e->comm_rank = rank;
+    e->comm_world = world;
+    return VC_OK;
+}
+
+int vc_comm_destroy(vc_engine* e) {
+    if (!e) return VC_ERR_ARG;
+    if (!e->comm) return VC_OK;
+    const NcclApi* api = load_nccl();
+    cudaSetDevice(e->g.device);
+    cudaStreamSynchronize(e->stream);
+    if (api) api->CommDestroy(e->comm);
+    e->comm = nullptr;
+    e->comm_rank = 0; e->comm_world = 1;
+    return VC_OK;
+}
+
+int vc_comm_info(const vc_engine* e, int32_t* rank, int32_t* world, int32_t* nccl_version) {
+    if (!e || !rank || !world || !nccl_version) return VC_ERR_ARG;
+    *rank = e->comm ? e->comm_rank : 0;
+    *world = e->comm ? e->comm_world : 1;
+    *nccl_version = e->comm ? g_nccl.version : 0;
+    return VC_OK;
+}
+
+int vc_exchange_halos(vc_engine* e) {
+    if (!e) return VC_ERR_ARG;
+    if (!e->comm) return fail(e, VC_ERR_STATE, "vc_exchange_halos: no communicator (vc_comm_init)");
+    const NcclApi* api = load_nccl();
+    if (bind_device(e)) return VC_ERR_CUDA;
+    int rc = materialize_reset(e);
+    if (rc) return rc;
+    // slabs are in rank order along z (rank r below rank r + 1): my first plane goes down, my last plane goes up
+    const bool down = e->comm_rank > 0 && e->g.z_begin > 0, up = e->comm_rank + 1 < e->comm_world && e->g.z_end < e->g.Z;
+    const size_t n = (size_t)e->plane_words;
+    VC_NCCL(e, api, api->GroupStart());
+    if (down) {
+        VC_NCCL(e, api, api->Send(e->occ_slab(), n, ncclUint32, e->comm_rank - 1, e->comm, e->stream));
+        VC_NCCL(e, api, api->Recv(halo_slot(e, 0), n, ncclUint32, e->comm_rank - 1, e->comm, e->stream));
+    }
+    if (up) {
+        VC_NCCL(e, api, api->Send(e->occ_slab() + e->slab_words - e->plane_words, n, ncclUint32, e->comm_rank + 1, e->comm, e->stream));
+        VC_NCCL(e, api, api->Recv(halo_slot(e, 1), n, ncclUint32, e->comm_rank + 1, e->comm, e->stream));
+    }
+    VC_NCCL(e, api, api->GroupEnd());
+    if (down) e->halo_lo = true;
+    if (up) e->halo_hi = true;
+    e->have_colors = false;
+    e->have_mc = false;
+    return VC_OK;
+}
+
+int vc_gather(vc_engine* e, int32_t what, const int32_t* z_bounds) {
+    if (!e) return VC_ERR_ARG;
+    if (!e->comm) return fail(e, VC_ERR_STATE, "vc_gather: no communicator (vc_comm_init)");
+    if (!(what & 3) || (what & ~3) || !z_bounds) return fail(e, VC_ERR_ARG, "vc_gather: what = 1 (occupied), 2 (seen) or 3 (both), with the world + 1 slab boundaries");
+    if (!e->d_occ_full) return fail(e, VC_ERR_STATE, "vc_gather: needs whole-grid buffers (vc_alloc_full_volumes or vc_bind_volumes)");
+    const int R = e->comm_world, r = e->comm_rank;
+    if (z_bounds[0] != 0 || z_bounds[R] != e->g.Z || z_bounds[r] != e->g.z_begin || z_bounds[r + 1] != e->g.z_end)
+        return fail(e, VC_ERR_ARG, "vc_gather: z_bounds do not cover [0,%d) with slab %d = [%d,%d)", e->g.Z, r, e->g.z_begin, e->g.z_end);
+    bool equal = true;
+    for (int k = 0; k < R; k++) {
+        if (z_bounds[k + 1] <= z_bounds[k]) return fail(e, VC_ERR_ARG, "vc_gather: empty slab %d", k);
+        equal = equal && (z_bounds[k + 1] - z_bounds[k] == z_bounds[1] - z_bounds[0]);
+    }
+    const NcclApi* api = load_nccl();
+    if (bind_device(e)) return VC_ERR_CUDA;
+    int rc = materialize_reset(e);
+    if (rc) return rc;
+    const size_t pw = (size_t)e->plane_words;
+    for (int vol = 0; vol < 2; vol++) {
+        if (!(what & (1 << vol))) continue;
+        uint32_t* full = vol == 0 ? e->d_occ_full : e->d_seen_full;
+        if (equal) {  // in place: my slab already sits at rank * count
+            VC_NCCL(e, api, api->AllGather(full + (size_t)z_bounds[r] * pw, full, (size_t)(z_bounds[1] - z_bounds[0]) * pw, ncclUint32, e->comm, e->stream));
+        } else {      // ragged (balanced) slabs: every rank sends its slab to every other one, all transfers in one group
+            VC_NCCL(e, api, api->GroupStart());
+            for (int k = 0; k < R; k++) {
+                if (k == r) continue;
+                VC_NCCL(e, api, api->Send(full + (size_t)z_bounds[r] * pw, (size_t)(z_bounds[r + 1] - z_bounds[r]) * pw, ncclUint32, k, e->comm, e->stream));
+                VC_NCCL(e, api, api->Recv(full + (size_t)z_bounds[k] * pw, (size_t)(z_bounds[k + 1] - z_bounds[k]) * pw, ncclUint32, k, e->comm, e->stream));
+            }
+            VC_NCCL(e, api, api->GroupEnd());
+        }
+    }
+    if (what & 1) { e->gathered = true; e->have_colors = false; e->have_mc = false; }
+    return VC_OK;
+}
+
+int vc_download_full(vc_engine* e, int32_t which, uint32_t* words, uint64_t n_words) {
+    if (!e || !words || (which != 0 && which != 1)) return VC_ERR_ARG;
+    if (!e->d_occ_full) return fail(e, VC_ERR_STATE, "vc_download_full: no whole-grid buffers (vc_alloc_full_volumes / vc_bind_volumes)");
+    if (which == 0 && !e->gathered && !e->whole_grid()) return fail(e, VC_ERR_STATE, "vc_download_full: the grid has not been gathered (vc_gather / vc_set_gathered)");
+    const uint64_t n = (uint64_t)e->g.Z * (uint64_t)e->plane_words;
+    if (n_words < n) return fail(e, VC_ERR_CAPACITY, "vc_download_full: buffer holds %llu words, the grid has %llu", (unsigned long long)n_words, (unsigned long long)n);
+    if (bind_device(e)) return VC_ERR_CUDA;
+    int rc = materialize_reset(e);
+    if (rc) return rc;
+    VC_CUDA(e, cudaMemcpyAsync(words, which == 0 ? e->d_occ_full : e->d_seen_full, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return VC_OK;
+}
+
+int vc_comm_allreduce_u64(vc_engine* e, uint64_t* values, int32_t n) {
+    if (!e || !values || n < 1) return VC_ERR_ARG;
+    if (!e->comm) return VC_OK;  // a single engine: the sum is the value
+    const NcclApi* api = load_nccl();
+    if (bind_device(e)) return VC_ERR_CUDA;
+    if (e->reduce_cap < (size_t)n) {
+        VC_CUDA(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_reduce); e->d_reduce = nullptr; e->reduce_cap = 0;
+        VC_CUDA(e, cudaMalloc(&e->d_reduce, (size_t)n * 8));
+        e->reduce_cap = (size_t)n;
+    }
+    VC_CUDA(e, cudaMemcpyAsync(e->d_reduce, values, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+    VC_NCCL(e, api, api->AllReduce(e->d_reduce, e->d_reduce, (size_t)n, ncclUint64, ncclSum, e->comm, e->stream));
+    VC_CUDA(e, cudaMemcpyAsync(values, e->d_reduce, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    VC_CUDA(e, cudaStreamSynchronize(e->stream));
     return VC_OK;
 }
 

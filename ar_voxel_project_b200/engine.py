@@ -226,6 +226,59 @@ class VoxelEngine:
     def set_gathered(self, flag=True):
         self._check(self._lib.vc_set_gathered(self._h, int(bool(flag))))
 
+    def alloc_full_volumes(self):
+        """engine-owned whole-grid buffers (what gather() fills); resets the state"""
+        self._check(self._lib.vc_alloc_full_volumes(self._h))
+
+    # one-plane halos of `occupied` (what the colour / cube-index passes of a slab need from its neighbours)
+    def halo_words(self):
+        n = C.c_uint64()
+        self._check(self._lib.vc_halo_words(self._h, C.byref(n)))
+        return n.value
+
+    def export_halo(self, which):
+        """device pointer of the slab's first (0) / last (1) plane"""
+        p = C.c_void_p()
+        self._check(self._lib.vc_export_halo(self._h, int(which), C.byref(p)))
+        return p.value
+
+    def import_halo(self, which, device_ptr):
+        """copy a neighbour's plane into plane z_begin - 1 (which = 0) / z_end (which = 1); None drops it"""
+        self._check(self._lib.vc_import_halo(self._h, int(which), C.c_void_p(device_ptr or 0)))
+
+    # NCCL communicator inside libvoxcarve.so: one rank per GPU, slabs in rank order along z
+    def comm_init(self, rank, world, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.vc_comm_init(self._h, int(rank), int(world), buf))
+
+    def comm_destroy(self):
+        self._check(self._lib.vc_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.vc_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def exchange_halos(self):
+        self._check(self._lib.vc_exchange_halos(self._h))
+
+    def gather(self, bounds, occupied=True, seen=False):
+        """assemble the whole grid in the bound / engine-owned whole-grid buffers of every rank (in place, over NCCL)"""
+        b = (C.c_int32 * len(bounds))(*[int(x) for x in bounds])
+        self._check(self._lib.vc_gather(self._h, (1 if occupied else 0) | (2 if seen else 0), b))
+
+    def download_full(self, which=0):
+        """the whole (gathered) grid out of the whole-grid buffers: which = 0 occupied, 1 seen -> uint32[Z, Y, Wx]"""
+        out = np.empty((self.Z, self.Y, self.Wx), np.uint32)
+        self._check(self._lib.vc_download_full(self._h, int(which), C.c_void_p(out.ctypes.data), out.size))
+        return out
+
+    def allreduce_u64(self, values):
+        """element-wise sum over the ranks of the communicator -> numpy uint64 (identity without a communicator)"""
+        a = np.ascontiguousarray(values, np.uint64).copy()
+        self._check(self._lib.vc_comm_allreduce_u64(self._h, C.c_void_p(a.ctypes.data), a.size))
+        return a
+
     def upload_volumes(self, occ_words, seen_words):
         n = (self.z_end - self.z_begin) * self.Y * self.Wx
         a, ka = _host_ptr(occ_words, np.uint32, n * 4, "occupied words")
@@ -308,6 +361,26 @@ class VoxelEngine:
         s = L.Stats()
         self._check(self._lib.vc_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by rank 0 and handed to every rank's VoxelEngine.comm_init"""
+    lib = L.load()
+    buf = C.create_string_buffer(128)
+    rc = lib.vc_comm_unique_id(buf)
+    if rc != L.VC_OK:
+        raise VoxCarveError(rc, lib.vc_last_error(None).decode())
+    return buf.raw
+
+
+def exchange_halos_peer(engines):
+    """engines of THIS process whose slabs tile a z-range: everyone receives its neighbours' boundary planes (device copies)"""
+    lib = L.load()
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    rc = lib.vc_exchange_halos_peer(arr, len(engines))
+    if rc != L.VC_OK:
+        bad = [e for e in engines if e._lib.vc_last_error(e._h)]
+        raise VoxCarveError(rc, "; ".join(e._lib.vc_last_error(e._h).decode() for e in bad))
 
 
 def measure_peaks(device=0):

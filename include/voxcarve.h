@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VC_API_VERSION 2
+#define VC_API_VERSION 3
 
 #if defined(__GNUC__)
 #define VC_EXPORT __attribute__((visibility("default")))
@@ -44,7 +44,8 @@ enum vc_status {
     VC_ERR_ARG = 1,      /* bad argument (message in vc_last_error) */
     VC_ERR_CUDA = 2,     /* CUDA runtime error, or no device */
     VC_ERR_STATE = 3,    /* call order: views/masks/images not set, halo planes missing, ... */
-    VC_ERR_CAPACITY = 4  /* caller buffer too small */
+    VC_ERR_CAPACITY = 4, /* caller buffer too small */
+    VC_ERR_COMM = 5      /* NCCL: library not loadable, or a collective failed */
 };
 
 /* Grid = Model(x, y, z, size) (Model.h:108, Model.cpp:9-14) restricted to the z-slab
@@ -168,6 +169,46 @@ VC_EXPORT int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_
 VC_EXPORT int vc_device_volumes(vc_engine* e, void** d_occupied_slab, void** d_seen_slab);
 /* declare that planes outside the slab held in a bound full volume are valid (after the gather) */
 VC_EXPORT int vc_set_gathered(vc_engine* e, int32_t gathered);
+
+/* Whole-grid buffers owned by the engine (instead of caller-owned ones, vc_bind_volumes): what vc_gather fills. Resets the state. */
+VC_EXPORT int vc_alloc_full_volumes(vc_engine* e);
+
+/* One-plane halos.  The consumers of a slab read ONE neighbour plane of `occupied` on each side: isInner of the colour pass
+ * (Model.h:126-132) planes z_begin - 1 and z_end, the cube index (MarchingCubes.h:537-552) plane z_end.  A plane is Y*Wx words
+ * (vc_halo_words).  Planes outside the grid are empty by definition (Model::get, Model.h:119-124) and never exchanged.
+ * Imported halos stay valid until this engine carves / resets / uploads again (its neighbours then carve again too).
+ *   vc_export_halo: device pointer of the slab's own first (which = 0) or last (which = 1) plane.
+ *   vc_import_halo: copy a plane (device pointer on any GPU of this process; the copy runs on this engine's stream, the
+ *                   caller orders it after the producer) into plane z_begin - 1 (which = 0) or z_end (which = 1); NULL drops it.
+ *   vc_exchange_halos_peer: all engines of ONE process (any devices, any order; their slabs must tile a z-range): every
+ *                   engine receives its neighbours' boundary planes, ordered after the producers' streams by events.
+ *   vc_exchange_halos: the same across processes / threads over NCCL send/recv, rank r holding the slab below rank r + 1. */
+VC_EXPORT int vc_halo_words(const vc_engine* e, uint64_t* n_words);
+VC_EXPORT int vc_export_halo(vc_engine* e, int32_t which, void** d_plane);
+VC_EXPORT int vc_import_halo(vc_engine* e, int32_t which, const void* d_plane);
+VC_EXPORT int vc_exchange_halos_peer(vc_engine** engines, int32_t n);
+
+/* NCCL communicator of the engines that share one grid, one rank per GPU, slabs in rank order along z (SURVEY §8b "gather()").
+ * libnccl.so.2 is loaded at run time, the first time one of these is called (a copy the process already carries - a
+ * Python framework may bundle its own - is shared); VC_ERR_COMM if it cannot be.  Rank 0 makes the 128-byte id with vc_comm_unique_id and hands it to
+ * the other ranks by any means (MPI, a file, a socket); vc_comm_init blocks until all `world` ranks have called it.
+ *   vc_exchange_halos: see above.  One grouped send/recv pair per neighbour on the engine's stream; returns without waiting.
+ *   vc_gather: assemble the whole grid in place in the whole-grid buffers (vc_alloc_full_volumes / vc_bind_volumes) of
+ *     every rank.  what: 1 = occupied, 2 = seen, 3 = both; z_bounds = the world + 1 slab boundaries (vc_plan_slabs).  Equal
+ *     slabs: one in-place ncclAllGather per volume; balanced (ragged) slabs: one group of sends / receives per volume.
+ *     Marks the grid gathered (vc_set_gathered) when `occupied` was included.  Only a consumer that needs every voxel - the
+ *     host Model, fastCarve's flood - needs this; colour and cube-index passes need the halos only.
+ *   vc_comm_allreduce_u64: element-wise sum of n host counters over the ranks (cube-index histograms, voxel counts). */
+VC_EXPORT int vc_comm_unique_id(void* unique_id_128);
+VC_EXPORT int vc_comm_init(vc_engine* e, int32_t rank, int32_t world, const void* unique_id_128);
+VC_EXPORT int vc_comm_destroy(vc_engine* e);
+VC_EXPORT int vc_comm_info(const vc_engine* e, int32_t* rank, int32_t* world, int32_t* nccl_version);
+VC_EXPORT int vc_exchange_halos(vc_engine* e);
+VC_EXPORT int vc_gather(vc_engine* e, int32_t what, const int32_t* z_bounds);
+VC_EXPORT int vc_comm_allreduce_u64(vc_engine* e, uint64_t* values, int32_t n);
+/* The WHOLE grid (Z*Y*Wx words) out of the whole-grid buffers into HOST memory: which = 0 occupied (must have been gathered),
+ * 1 seen (gathered by the caller's choice of vc_gather's `what`).  What the shim fills a host Model from after vc_gather. */
+VC_EXPORT int vc_download_full(vc_engine* e, int32_t which, uint32_t* words, uint64_t n_words);
 
 /* ---- outputs (HOST buffers, caller-allocated) ------------------------------------ */
 VC_EXPORT int vc_slab_words(const vc_engine* e, uint64_t* n_words); /* (z_end-z_begin)*Y*Wx */

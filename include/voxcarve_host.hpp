@@ -17,11 +17,13 @@
 #ifndef VOXCARVE_HOST_HPP
 #define VOXCARVE_HOST_HPP
 
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -118,6 +120,23 @@ class Engine {
         check(vc_download_mesh(h_, verts.data(), rgb.data(), n));
         return n;
     }
+    // multi-GPU plumbing: balanced z-slabs, one-plane halos, NCCL collectives inside the library (voxcarve.h)
+    std::vector<int32_t> planSlabs(int n_parts) { std::vector<int32_t> b((size_t)n_parts + 1); check(vc_plan_slabs(h_, n_parts, b.data())); return b; }
+    void setSlab(int z_begin, int z_end) { check(vc_set_slab(h_, z_begin, z_end)); check(vc_slab_words(h_, &words_)); }
+    void allocFullVolumes() { check(vc_alloc_full_volumes(h_)); }
+    void commInit(int rank, int world, const void* unique_id_128) { check(vc_comm_init(h_, rank, world, unique_id_128)); }
+    void exchangeHalos() { check(vc_exchange_halos(h_)); }
+    void gather(const std::vector<int32_t>& z_bounds, int what = 1) { check(vc_gather(h_, what, z_bounds.data())); }
+    void allreduce(uint64_t* values, int n) { check(vc_comm_allreduce_u64(h_, values, n)); }
+    std::vector<uint32_t> downloadFull(int which) {
+        std::vector<uint32_t> w((size_t)Z_ * Y_ * wordsPerRow());
+        check(vc_download_full(h_, which, w.data(), w.size()));
+        return w;
+    }
+    void synchronize() { check(vc_synchronize(h_)); }
+    // download this slab's volumes into caller memory (e.g. at the slab's offset inside whole-grid host vectors)
+    void carveDownloadInto(uint32_t* occ, uint32_t* seen, int mode = VC_EXACT) { check(vc_carve_download(h_, mode, occ, seen, words_)); }
+    uint64_t slabWords() const { return words_; }
     vc_stats stats() { vc_stats s{}; check(vc_get_stats(h_, &s)); return s; }
     vc_engine* handle() { return h_; }
     int wordsPerRow() const { return (X_ + 31) / 32; }
@@ -238,6 +257,45 @@ void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = fals
     } else {
         e.carveDownload(occ, seen);
     }
+    detail::applyCarve(model, occ, seen);
+    std::cout << "LOG - VC: carving complete." << std::endl;
+}
+
+// carve() on several GPUs of this host: the grid is cut into balanced z-slabs (vc_plan_slabs), one engine and one host
+// thread per device, every engine sees all views; each slab goes straight from its GPU into its place in the whole-grid host
+// words (one PCIe link per GPU, no device-to-device traffic: a host Model needs no all-gather).  Same Model as carve().
+template <class ModelT>
+void carveOnDevices(const ViewCache& views, ModelT& model, const std::vector<int>& devices) {
+    if (devices.size() <= 1) {
+        carve(views, model);
+        return;
+    }
+    std::cout << "LOG - VC: starting carving process (version 1)." << std::endl;
+    const int X = model.getX(), Y = model.getY(), Z = model.getZ(), n = (int)std::min<size_t>(devices.size(), (size_t)Z);
+    const float size = model.getSize();
+    const size_t plane = (size_t)Y * ((X + 31) / 32);
+    std::vector<uint32_t> occ(plane * Z), seen(plane * Z);
+    std::vector<int32_t> bounds;
+    {
+        Engine planner(X, Y, Z, size, 0, -1, devices[0]);
+        planner.setViews(views, false);
+        bounds = planner.planSlabs(n);
+    }
+    std::vector<std::string> errors((size_t)n);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < n; r++)
+        threads.emplace_back([&, r] {
+            try {
+                Engine e(X, Y, Z, size, bounds[r], bounds[r + 1], devices[r]);
+                e.setViews(views, false);
+                e.carveDownloadInto(occ.data() + plane * bounds[r], seen.data() + plane * bounds[r]);
+            } catch (const std::exception& ex) {
+                errors[r] = ex.what();
+            }
+        });
+    for (auto& t : threads) t.join();
+    for (const auto& m : errors)
+        if (!m.empty()) throw Error(VC_ERR_CUDA, m);
     detail::applyCarve(model, occ, seen);
     std::cout << "LOG - VC: carving complete." << std::endl;
 }

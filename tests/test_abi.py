@@ -10,7 +10,7 @@ from conftest import ROOT, _has_gpu
 
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "voxcarve.h")).read()
-    return sorted(set(re.findall(r"VC_EXPORT[^;]*?\b(vc_[a-z_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"VC_EXPORT[^;]*?\b(vc_[a-z0-9_]+)\s*\(", hdr)))
 
 
 def test_header_declares_the_boundary():
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 def test_binding_covers_header_exactly(lib_built):
     from ar_voxel_project_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
-    assert _lib.load().vc_api_version() == 2
+    assert _lib.load().vc_api_version() == 3
 
 
 def test_no_torch_types_in_abi():

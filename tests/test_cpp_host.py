@@ -9,17 +9,18 @@ import pytest
 from conftest import GOLDEN, ROOT
 
 
-def _build(tmp_path, lib_built):
-    exe = str(tmp_path / "host_roundtrip")
+def _build(tmp_path, lib_built, name="host_roundtrip"):
+    exe = str(tmp_path / name)
     libdir = os.path.dirname(lib_built)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "host_roundtrip.cpp"), "-o", exe,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
                            "-L", libdir, "-lvoxcarve", f"-Wl,-rpath,{libdir}"])
     return exe
 
 
 def test_host_layer_compiles_without_opencv(tmp_path, lib_built):
     assert os.path.exists(_build(tmp_path, lib_built))
+    assert os.path.exists(_build(tmp_path, lib_built, "multi_gpu"))
     # the OpenCV shim must at least be syntactically inert where OpenCV is absent
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c++",
                            os.path.join(ROOT, "include", "voxcarve_shim.hpp")])
@@ -96,3 +97,36 @@ def test_cpp_pipeline_matches_oracle(tmp_path, lib_built, oracle):
     ref = tmp_path / "ref.off"
     oracle.write_off(str(ref), rv, rc, np.float32(1.5) * s, (0.5, -0.25, 2.0))
     assert open(off).read() == open(ref).read()
+
+
+@pytest.mark.gpu
+def test_cpp_host_drives_several_engines(tmp_path, lib_built, oracle):
+    """a C++ host (no Python, no torch in the process) runs more than one engine: one thread + one NCCL rank per
+    visible GPU through vc_comm_init / vc_exchange_halos / vc_comm_allreduce_u64 / vc_gather when there are >= 2 GPUs, several
+    engines on device 0 with vc_exchange_halos_peer otherwise; slab results, summed histograms, concatenated colour records, the
+    gathered grid and vc::carveOnDevices' Model all equal the single engine's - which equals the oracle's."""
+    import torch
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 90, 50, 70
+    w = Workload(90, 7, 256, 192, seed=9, dims=(X, Y, Z))
+    case = tmp_path / "case.bin"
+    with open(case, "wb") as f:
+        np.array([X, Y, Z, w.V, w.W, w.H], np.int32).tofile(f)
+        np.array([w.s], np.float32).tofile(f)
+        w.P.astype(np.float32).tofile(f)
+        w.M.astype(np.float32).tofile(f)
+        w.mask_bits.astype(np.uint32).tofile(f)
+        w.images_bgr().astype(np.uint8).tofile(f)
+    n_dev = torch.cuda.device_count()
+    n_slabs = min(n_dev, 4) if n_dev >= 2 else 3
+    out = tmp_path / "out.bin"
+    r = subprocess.run([_build(tmp_path, lib_built, "multi_gpu"), str(case), str(n_dev), str(n_slabs), str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    raw = open(out, "rb").read()
+    n = Z * Y * ((X + 31) // 32)
+    occ = np.frombuffer(raw, np.uint32, n).reshape(Z, Y, -1)
+    seen = np.frombuffer(raw, np.uint32, n, n * 4).reshape(Z, Y, -1)
+    hist = np.frombuffer(raw, np.uint64, 256, n * 8)
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+    assert np.array_equal(hist, oracle.mc_classify(X, Y, Z, ro)[0])

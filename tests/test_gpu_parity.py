@@ -774,3 +774,108 @@ def test_engines_sharing_a_device_keep_their_own_views(A, oracle):
             idx, rgbn = e.download_colors()
             ridx, rrgbn = oracle.color(X, Y, Z, w.s, w.P, w.M, w.W, w.H, w.images_bgr(), r[0], mode)
             assert np.array_equal(idx, ridx) and np.array_equal(rgbn, rrgbn)
+
+
+def _whole_grid_reference(A, w, X, Y, Z, with_images=True):
+    """single-engine results of the consumers on the whole grid: occupied, seen, cube-index histogram, colour records (avg, closest)"""
+    with A.VoxelEngine(X, Y, Z, w.s) as e:
+        e.set_views(w.P, w.W, w.H, w.M)
+        e.set_masks_bits(w.mask_bits)
+        e.carve()
+        occ, seen = e.download_occupied(), e.download_seen()
+        e.mc_classify()
+        hist, na, nt = e.download_mc()
+        cols = {}
+        if with_images:
+            e.set_images(w.images_bgr())
+            for mode in (2, 1):
+                e.color(mode)
+                cols[mode] = e.download_colors()
+    return occ, seen, hist, nt, cols
+
+
+@pytest.mark.parametrize("bounds", [[0, 13, 40], [0, 8, 9, 24, 40], [0, 1, 2, 40]])
+def test_one_plane_halos_replace_the_gather_for_colour_and_cube_index(A, oracle, bounds):
+    """the consumers of a slab need ONE neighbour plane of `occupied` on each side, not the whole grid.  Engines on
+    slabs (incl. one-plane slabs) of one device swap those planes (vc_exchange_halos_peer); their cube-index histograms then sum
+    to the whole grid's and their colour records concatenate to it, bit for bit - with slab-sized AND with bound whole-grid volumes."""
+    import torch
+    from ar_voxel_project_b200.engine import exchange_halos_peer
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 70, 44, 40
+    w = Workload(70, 6, 240, 180, seed=5, dims=(X, Y, Z))
+    occ, seen, hist, nt, cols = _whole_grid_reference(A, w, X, Y, Z)
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+    rh, _, rnt = oracle.mc_classify(X, Y, Z, ro)
+    assert np.array_equal(hist, rh) and nt == rnt
+    for bound_full in (False, True):
+        engines, fulls = [], []
+        try:
+            for z0, z1 in zip(bounds[:-1], bounds[1:]):
+                e = A.VoxelEngine(X, Y, Z, w.s, z_begin=z0, z_end=z1)
+                engines.append(e)
+                if bound_full:  # every engine its own whole-grid buffer, as separate GPUs would have; garbage outside the slab
+                    f = [torch.randint(-2 ** 31, 2 ** 31 - 1, (Z, Y, (X + 31) // 32), dtype=torch.int32, device="cuda") for _ in range(2)]
+                    fulls.append(f)
+                    e.bind_volumes(f[0].data_ptr(), f[1].data_ptr())
+                e.set_views(w.P, w.W, w.H, w.M)
+                e.set_masks_bits(w.mask_bits)
+                e.set_images(w.images_bgr())
+                e.carve()
+            if len(engines) > 1:
+                with pytest.raises(A.VoxCarveError):   # no halos yet: a slab cannot classify its last cell plane
+                    engines[0].mc_classify()
+            exchange_halos_peer(engines[::-1])          # any order
+            tot = np.zeros(256, np.uint64)
+            for e in engines:
+                e.mc_classify()
+                tot += e.download_mc()[0]
+            assert np.array_equal(tot, hist), f"cube-index histograms of the slabs do not sum to the grid's (bound_full={bound_full})"
+            for mode in (2, 1):
+                idx, rgbn = [], []
+                for e in engines:
+                    e.color(mode)
+                    i, c = e.download_colors()
+                    idx.append(i), rgbn.append(c)
+                assert np.array_equal(np.concatenate(idx), cols[mode][0]) and np.array_equal(np.concatenate(rgbn), cols[mode][1])
+            assert np.array_equal(np.concatenate([e.download_occupied() for e in engines]), occ)
+            # a new carve invalidates the imported planes
+            engines[0].reset(), engines[0].carve()
+            if len(engines) > 1:
+                with pytest.raises(A.VoxCarveError):
+                    engines[0].mc_classify()
+            # explicit export / import of single planes does the same job (here through device pointers of the same GPU)
+            if len(engines) > 1:
+                engines[0].synchronize(), engines[1].synchronize()
+                engines[0].import_halo(1, engines[1].export_halo(0))
+                engines[0].mc_classify()
+                with pytest.raises(A.VoxCarveError):
+                    engines[0].import_halo(0, engines[1].export_halo(0))  # plane -1 is outside the grid
+        finally:
+            for e in engines:
+                e.close()
+
+
+def test_nccl_two_ranks_halos_gather_bitwise(A, tmp_path):
+    """VERDICT r1 #1c: two processes, one GPU each, NCCL inside libvoxcarve.so (vc_comm_init / vc_exchange_halos / vc_gather /
+    vc_comm_allreduce_u64): planned (ragged) slabs are carved, halos exchanged, consumers run on the slabs, the grid gathered -
+    and every word compared with the single-GPU result and oracle planes (tests/nccl_slab_worker.py writes the verdicts)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (NCCL refuses two ranks on one device); run with gpurun --gpus 2 - log kept in profiles/")
+    from conftest import ROOT
+    port = 29500 + os.getpid() % 2000
+    out = tmp_path / "nccl"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "nccl_slab_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for rank in range(2):
+        v = json.load(open(out / f"rank{rank}.json"))
+        assert v["ok"], v
+        assert v["world"] == 2 and v["nccl_version"] > 0
