@@ -434,7 +434,7 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
     if (bind_device(e)) return VC_ERR_CUDA;
     if (!e->d_mask) VC_CUDA(e, cudaMalloc(&e->d_mask, e->mask_bytes));
     if (format == VC_MASK_BITS) {
-        VC_CUDA(e, cudaMemcpyAsync(e->d_mask, masks, e->mask_bytes, cudaMemcpyHostToDevice, e->stream));
+        VC_CUDA(e, cudaMemcpyAsync(e->d_mask, masks, e->mask_bytes, cudaMemcpyDefault, e->stream));  // host or device memory
     } else {
         const size_t bytes = (size_t)e->V * e->H * e->W * 3;
         if (e->bgr_tmp_bytes < bytes) {

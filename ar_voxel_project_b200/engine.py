@@ -147,6 +147,10 @@ class VoxelEngine:
         self._check(self._lib.vc_set_masks(self._h, C.c_void_p(addr), L.VC_MASK_BITS))
         self._keep = [keep]
 
+    def set_masks_bits_device(self, device_ptr):
+        """bit-packed silhouettes already on the GPU (same layout): device-to-device copy + summed-area tables, no host sync"""
+        self._check(self._lib.vc_set_masks(self._h, C.c_void_p(int(device_ptr)), L.VC_MASK_BITS))
+
     def set_calibration(self, K, dist):
         """camera matrix (3x3) and distortion coefficients (4, 5 or 8) for the on-device cv::undistort"""
         K = np.ascontiguousarray(K, np.float64).reshape(9)

@@ -149,3 +149,27 @@ CONFIGS = {  # BASELINE.json configs[2..4]
     "C4": dict(N=1024, V=72, W=1920, H=1080),
     "C5": dict(N=2048, V=72, W=3840, H=2160),
 }
+
+
+def noisy_masks(w, seed=0, p_noise=0.01, fringe=2):
+    """Hostile version of a workload's silhouettes, as 8UC3 masks (the form the reference holds them in, VoxelCarving.cpp:36):
+    a ragged `fringe`-pixel band of JPEG-like greys around every silhouette edge (30 % of the band exactly black) plus
+    `p_noise` salt-and-pepper (half black holes inside the object, half white specks in the background; SURVEY §8c-8 measured
+    0.5-1.3 % non-binary pixels on the real masks).  Only (0,0,0) carves (VoxelCarving.cpp:49-50).
+    -> (uint8[V][H][W][3], the bit masks they pack to)"""
+    from scipy import ndimage
+    rng = np.random.default_rng(seed + 12345)
+    fg = ~unpack_bits(w.mask_bits, w.W)
+    out = np.empty((w.V, w.H, w.W, 3), np.uint8)
+    for v in range(w.V):
+        f = fg[v]
+        g = f.astype(np.uint8) * 255
+        band = ndimage.binary_dilation(f, iterations=fringe) & ~ndimage.binary_erosion(f, iterations=fringe)
+        r = rng.integers(0, 256, size=f.shape, dtype=np.uint8)
+        r[rng.random(f.shape) < 0.3] = 0
+        g[band] = r[band]
+        n = rng.random(f.shape)
+        g[n < p_noise / 2] = 0
+        g[(n >= p_noise / 2) & (n < p_noise)] = 255
+        out[v] = g[..., None]
+    return out, pack_bits((out == 0).all(-1))

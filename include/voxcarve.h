@@ -112,7 +112,9 @@ VC_EXPORT int vc_synchronize(vc_engine* e);
 VC_EXPORT int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, const float* M);
 /* Undistorted silhouette masks (VoxelCarving.cpp:36). VC_MASK_BITS: uint32[V][H][ceil(W/32)],
  * bit x&31 of word x>>5, 1 = background (pixel == (0,0,0), VoxelCarving.cpp:50).
- * VC_MASK_BGR8: the 8UC3 images themselves, uint8[V][H][W][3]; packed on the device. HOST memory. */
+ * VC_MASK_BGR8: the 8UC3 images themselves, uint8[V][H][W][3]; packed on the device. HOST memory (VC_MASK_BITS also takes a
+ * DEVICE pointer: silhouettes that a segmentation stage left on the GPU).  Builds the summed-area tables of the silhouettes that
+ * VC_EXACT's classifier reads (three kernels, C4: 0.36 ms). */
 VC_EXPORT int vc_set_masks(vc_engine* e, const void* masks, int32_t format);
 /* Undistorted colour images 8UC3 BGR (ColorReconstruction.h:23), uint8[V][H][W][3], HOST memory. */
 VC_EXPORT int vc_set_images(vc_engine* e, const uint8_t* images_bgr);
