@@ -48,6 +48,8 @@ SIGNATURES = {
     "vc_reset": (C.c_int, [_P]),
     "vc_carve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vc_carve_download": (C.c_int, [_P, C.c_int32, _P, _P, C.c_uint64]),
+    "vc_sparse_dims": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "vc_carve_download_sparse": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "vc_fast_carve": (C.c_int, [_P, C.c_int32]),
     "vc_color": (C.c_int, [_P, C.c_int32]),
     "vc_mc_classify": (C.c_int, [_P]),

@@ -199,6 +199,59 @@ class VoxelEngine:
         self._check(self._lib.vc_carve_download(self._h, mode, C.c_void_p(a), C.c_void_p(b), n))
         return out_occ, out_seen
 
+    def carve_download_sparse(self, flags=None, listed=None, words=None):
+        """fresh carve (reset implied) + download in sparse form: (flags uint8[nbz, nby, nbx], listed uint32[n], words uint32[n, 2, 64]).
+        Optional preallocated (e.g. pinned) buffers: flags of nbx*nby*nbz bytes, listed / words with room for the listed bricks."""
+        nbx, nby, nbz = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.vc_sparse_dims(self._h, C.byref(nbx), C.byref(nby), C.byref(nbz)))
+        nb = nbx.value * nby.value * nbz.value
+        own = flags is None
+        if own:
+            cap = max(1024, nb // 16)
+            flags, listed, words = np.empty(nb, np.uint8), np.empty(cap, np.uint32), np.empty(cap * 128, np.uint32)
+        else:
+            cap = min(listed.numel() if hasattr(listed, "numel") else listed.size, (words.numel() if hasattr(words, "numel") else words.size) // 128)
+        fa = flags.data_ptr() if hasattr(flags, "data_ptr") else flags.ctypes.data
+        n = C.c_uint64()
+        for attempt in range(2):
+            la = listed.data_ptr() if hasattr(listed, "data_ptr") else listed.ctypes.data
+            wa = words.data_ptr() if hasattr(words, "data_ptr") else words.ctypes.data
+            self.reset()
+            rc = self._lib.vc_carve_download_sparse(self._h, C.c_void_p(fa), nb, C.c_void_p(la), C.c_void_p(wa), cap, C.byref(n))
+            if rc == L.VC_ERR_CAPACITY and own and n.value > cap and attempt == 0:
+                cap = n.value
+                listed, words = np.empty(cap, np.uint32), np.empty(cap * 128, np.uint32)
+                continue
+            self._check(rc)
+            break
+        k = n.value
+        if hasattr(flags, "numpy"):
+            flags, listed, words = flags.numpy(), listed.numpy(), words.numpy()
+        return (flags[:nb].view(np.uint8).reshape(nbz.value, nby.value, nbx.value), listed[:k].view(np.uint32),
+                words[:k * 128].view(np.uint32).reshape(k, 2, 64))
+
+    def expand_sparse(self, flags, listed, words):
+        """sparse result -> (occupied, seen) uint32[nz, Y, Wx], the same words carve_download delivers (host side, numpy)"""
+        nz, Y, Wx, X = self.z_end - self.z_begin, self.Y, self.Wx, self.X
+        nbz, nby, nbx = flags.shape
+        valid = np.full(Wx, 0xffffffff, np.uint32)
+        if X % 32:
+            valid[-1] = (1 << (X % 32)) - 1
+        f = np.repeat(np.repeat(flags, 8, axis=0), 8, axis=1)[:nz, :Y]       # per (z, y, word)
+        occ = np.where(f & 1, np.uint32(0), valid[None, None, :]).astype(np.uint32)
+        seen = np.where(f & 2, valid[None, None, :], np.uint32(0)).astype(np.uint32)
+        if len(listed):
+            b = listed.astype(np.int64)
+            bx, by, bz = b % nbx, (b // nbx) % nby, b // (nbx * nby)
+            r = np.arange(64)
+            z = (bz[:, None] * 8 + r[None, :] // 8)
+            y = (by[:, None] * 8 + r[None, :] % 8)
+            ok = (z < nz) & (y < Y)
+            xx = np.broadcast_to(bx[:, None], z.shape)
+            occ[z[ok], y[ok], xx[ok]] = words[:, 0, :][ok]
+            seen[z[ok], y[ok], xx[ok]] = words[:, 1, :][ok]
+        return occ, seen
+
     def fast_carve(self, mode=L.VC_EXACT):
         self._check(self._lib.vc_fast_carve(self._h, mode))
 

@@ -9,8 +9,10 @@ BASELINE.json quotes the metric on (default C4: 1024^3 x 72 views, 1920x1080 sil
 `value`  = X*Y*Z*V (nominal voxel-view projections of the job) / device time, masks + their summed-area tables resident in HBM.
 `value_cold` = the same with the summed-area tables built inside the timed region (bit masks resident, vc_set_masks + carve).
 `value_with_consumer` = carve + (N > 1: one-plane halo exchange over NCCL) + cube-index classification of the slab, per step.
-`e2e`    = same metric through the C ABI with HOST buffers: per step H2D of P/M + the masks from pinned
-           memory, reset, carve, D2H of both bit volumes into pinned memory; wall clock, max over ranks.
+`e2e`    = same metric through the C ABI with HOST buffers: per step H2D of P/M + the masks from pinned memory, summed-area
+           tables, reset, carve, D2H of the result in sparse form (a flag byte per 32x8x8 brick + the words of the bricks that
+           were evaluated per voxel: the complete result, 1/25 of the bytes) into pinned memory; wall clock, max over ranks.
+           `e2e_dense` = the same with both bit volumes downloaded as plain words (PCIe-bound).
 `roofline` = projections executed by the dominant kernel (vc_carve_bricks: the corner projections of its 8x8x8 sub-brick
            classification + the per-voxel projections left after three levels of classification and the early exits)
            * 23 FLOP / that kernel's time against the measured FFMA peak of this GPU (CUDA-core bound, SURVEY §8d);
@@ -288,9 +290,13 @@ def run_small(args, reference_only=False):
                 e.dense_from_volumes(apply_colors=True, handle_unseen=True), e.synchronize()
                 g["model_on_device"] = wall(lambda: (e.dense_from_volumes(apply_colors=True, handle_unseen=True), e.synchronize()), 5)
 
-                def do_closure():
+                ts = []
+                for _ in range(4):   # applied ONCE to a freshly built Model, like main.cpp:297-299 (a second pass would dilate again); first round = warm-up
+                    e.dense_from_volumes(apply_colors=True, handle_unseen=True), e.synchronize()
+                    t = time.perf_counter()
                     e.dense_closure(3), e.synchronize()
-                g["closure"] = wall(do_closure, 1)   # applied once, like main.cpp:297-299 (a second pass would dilate again)
+                    ts.append((time.perf_counter() - t) * 1e3)
+                g["closure"] = float(np.median(ts[1:]))
                 def do_mc():
                     e.mc_mesh(0.5)
                 do_mc()
@@ -551,6 +557,7 @@ def run_ours(args):
     # what the CPU arm consumes too) and (b) the 8UC3 undistorted masks as the reference holds them in memory
     e2e = None
     e2e_bgr = None
+    e2e_dense = None
     if not args.no_e2e:
         out_occ = torch.empty((z1 - z0, Y, Wx), dtype=torch.int32).pin_memory()
         out_seen = torch.empty_like(out_occ).pin_memory()
@@ -578,14 +585,58 @@ def run_ours(args):
 
         s_bits = e2e_run(True)
         s_bgr = e2e_run(False)
-        # kernels per e2e step: [pack_bgr] + 3 SAT passes + 4 z-chunks x (2 classify + fill + carve_bricks)
-        e2e = {"value": nominal_total / s_bits, "unit": UNIT, "h2d_bytes_per_step": int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bits * 1e3,
+        # sparse result: one flag byte per 32x8x8 brick + the words of the bricks that were evaluated per voxel
+        nbz_, nby_, nbx_ = ((z1 - z0) + 7) // 8, (Y + 7) // 8, Wx
+        flags_p = torch.empty(nbz_ * nby_ * nbx_, dtype=torch.uint8).pin_memory()
+        cap = max(1024, flags_p.numel() // 4)
+        listed_p = torch.empty(cap, dtype=torch.int32).pin_memory()
+        words_p = torch.empty(cap * 128, dtype=torch.int32).pin_memory()
+        sparse_n = [0]
+
+        def one_sparse(use_bits=True):
+            eng.set_views(w.P, w.W, w.H, w.M)
+            if use_bits:
+                eng.set_masks_bits_async(bits_pinned)
+            else:
+                eng.set_masks_bgr(bgr, sync=False)
+            f_, l_, w_ = eng.carve_download_sparse(flags_p, listed_p, words_p)   # reset + carve + D2H of flags and listed words
+            sparse_n[0] = len(l_)
+            return f_, l_, w_
+
+        def sparse_run(use_bits):
+            for _ in range(2):
+                one_sparse(use_bits)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                one_sparse(use_bits)
+            barrier()
+            return allmax((time.perf_counter() - t0) / args.steps)
+        s_sparse = sparse_run(True)
+        s_sparse_bgr = sparse_run(False)
+        f_, l_, w_ = one_sparse()
+        t0 = time.perf_counter()
+        xo, xs = eng.expand_sparse(f_, l_, w_)
+        expand_ms = (time.perf_counter() - t0) * 1e3
+        eng.reset(), eng.carve()
+        sparse_ok = bool(np.array_equal(xo, eng.download_occupied()) and np.array_equal(xs, eng.download_seen()))
+        if not sparse_ok:
+            raise SystemExit("bench.py: the expanded sparse result differs from the dense volumes")
+        sparse_d2h = int(flags_p.numel() + sparse_n[0] * (4 + 512))
+        h2d_bits = int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes)
+        h2d_bgr = int(bgr.numel() + w.P.nbytes + w.M.nbytes)
+        # kernels per e2e step: [pack_bgr] + 3 SAT passes + 2 classify + carve_bricks + flag resolve + pack  (dense: 4 z-chunks x (2 classify + fill + carve_bricks))
+        e2e = {"value": nominal_total / s_sparse, "unit": UNIT, "h2d_bytes_per_step": h2d_bits, "d2h_bytes_per_step": sparse_d2h, "ms_per_step": s_sparse * 1e3,
                "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory",
-               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download", "gpu_launches": 15 * args.steps}
-        e2e_bgr = {"value": nominal_total / s_bgr, "unit": UNIT, "h2d_bytes_per_step": int(bgr.numel() + w.P.nbytes + w.M.nbytes),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": s_bgr * 1e3,
-                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "gpu_launches": 16 * args.steps}
+               "result": f"sparse: one flag byte per 32x8x8-voxel brick + occupied/seen words of the {sparse_n[0]} listed bricks (vc_carve_download_sparse); "
+                         "expands to exactly the dense volumes (checked after the timed region), which include/voxcarve_host.hpp applies to the Model brick by brick",
+               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download_sparse", "gpu_launches": 8 * args.steps,
+               "result_identical_to_dense": sparse_ok, "host_expand_numpy_ms_untimed": expand_ms}
+        e2e_bgr = {"value": nominal_total / s_sparse_bgr, "unit": UNIT, "h2d_bytes_per_step": h2d_bgr, "d2h_bytes_per_step": sparse_d2h, "ms_per_step": s_sparse_bgr * 1e3,
+                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "result": "sparse", "gpu_launches": 9 * args.steps}
+        e2e_dense = {"bits": {"value": nominal_total / s_bits, "ms_per_step": s_bits * 1e3, "h2d_bytes_per_step": h2d_bits, "d2h_bytes_per_step": int(d2h),
+                              "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download (both volumes as plain words, z-chunks overlapped with PCIe)", "gpu_launches": 15 * args.steps},
+                     "bgr8": {"value": nominal_total / s_bgr, "ms_per_step": s_bgr * 1e3, "h2d_bytes_per_step": h2d_bgr, "d2h_bytes_per_step": int(d2h), "gpu_launches": 16 * args.steps}}
         if noisy:   # the hostile masks only exist as 8UC3: that path is the headline e2e of this config
             e2e, e2e_bgr = e2e_bgr, e2e
         eng.set_masks_bits(w.mask_bits)
@@ -652,7 +703,7 @@ def run_ours(args):
                              "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}; "
                                     "write_only_floor_ms = the two volumes at the 3.68 TB/s a cudaMemset reaches on this GPU (tools/memset_bench.py)"},
             "gather": gather, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris, "color_ms": color_ms, "per_rank": per_rank,
-            "e2e": e2e, "e2e_bgr8": e2e_bgr, "gpu_launches": launches, "clocks": clk,
+            "e2e": e2e, "e2e_bgr8": e2e_bgr, "e2e_dense": e2e_dense, "gpu_launches": launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference(w, args.cpu_seconds, 1, 1)

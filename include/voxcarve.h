@@ -143,6 +143,18 @@ VC_EXPORT int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t v
 VC_EXPORT int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* seen, uint64_t n_words);
 /* (the overlap needs PAGE-LOCKED buffers - cudaHostAlloc / cudaHostRegister: a copy into pageable memory blocks the host, so with
  * pageable buffers the call degrades to the plain carve + two downloads.) */
+/* carve() over all views of a FRESH Model (vc_reset pending) + download of the result in SPARSE form: after a fresh carve
+ * most 32x8x8-voxel bricks are uniform (C4: 96 %) and one flag byte says everything about them; only the bricks the engine
+ * evaluated voxel by voxel need their words.  C4: 0.5 MB + 10 MB over PCIe instead of 268 MB.
+ *   brick_flags[b], b = bx + nbx*(by + nby*bz) (vc_sparse_dims; brick = voxels [32bx, 32bx+32) x [8by, 8by+8) x slab planes
+ *     [8bz, 8bz+8)): bit 0 (1) = every voxel carved (occupied 0, seen 1), bit 1 (2) = every voxel seen, bit 3 (8) = listed;
+ *     a brick that is neither carved nor listed is untouched (occupied 1), one that is not listed has seen = bit 1.
+ *   listed[i] = index of the i-th listed brick; words[128 i + r] = its occupied word of row r = 8*plane + y (0 outside the
+ *     grid), words[128 i + 64 + r] = its seen word.  n_listed > listed_capacity -> VC_ERR_CAPACITY (the volumes stay on the
+ *     device and vc_download_* still works).  include/voxcarve_host.hpp expands this into a Model or into plain words. */
+VC_EXPORT int vc_sparse_dims(const vc_engine* e, uint32_t* nbx, uint32_t* nby, uint32_t* nbz);
+VC_EXPORT int vc_carve_download_sparse(vc_engine* e, uint8_t* brick_flags, uint64_t flags_capacity, uint32_t* listed, uint32_t* words,
+                                       uint64_t listed_capacity, uint64_t* n_listed);
 /* fastCarve() (VoxelCarving.h:31, VoxelCarving.cpp:74-167): starts from the Model constructor state (it resets the
  * volumes itself) and needs the whole grid on this engine. */
 VC_EXPORT int vc_fast_carve(vc_engine* e, int32_t mode);

@@ -52,6 +52,16 @@ struct ViewCache {
     std::vector<double> dist;         // k1 k2 p1 p2 [k3 [k4 k5 k6]]
 };
 
+// Result of a fresh carve in sparse form (vc_carve_download_sparse): a flag byte per 32x8x8-voxel brick of the slab, and the
+// words of the listed bricks only.
+struct SparseCarve {
+    int X = 0, Y = 0, nz = 0;           // slab dimensions in voxels
+    uint32_t nbx = 0, nby = 0, nbz = 0;  // bricks
+    std::vector<uint8_t> flags;          // nbx*nby*nbz: 1 = carved whole, 2 = seen whole, 8 = listed
+    std::vector<uint32_t> listed;        // brick index of every listed brick
+    std::vector<uint32_t> words;         // 128 per listed brick: 64 occupied rows (8*plane + y), then 64 seen rows
+};
+
 struct McSummary {
     uint64_t hist[256];
     uint64_t active_cells, triangles;
@@ -88,6 +98,29 @@ class Engine {
         occ.resize(words_);
         seen.resize(words_);
         check(vc_carve_download(h_, mode, occ.data(), seen.data(), words_));
+    }
+    // fresh carve + sparse download (vc_reset is implied): 1/25 of the PCIe bytes of carveDownload on a 1024^3 grid
+    void carveDownloadSparse(SparseCarve& sp) {
+        check(vc_reset(h_));
+        check(vc_sparse_dims(h_, &sp.nbx, &sp.nby, &sp.nbz));
+        sp.X = X_; sp.Y = Y_; sp.nz = (int)(words_ / ((uint64_t)Y_ * wordsPerRow()));
+        const uint64_t nb = (uint64_t)sp.nbx * sp.nby * sp.nbz;
+        sp.flags.resize(nb);
+        uint64_t cap = std::max<uint64_t>(1024, nb / 16), n = 0;
+        for (int attempt = 0;; attempt++) {
+            sp.listed.resize(cap);
+            sp.words.resize(cap * 128);
+            const int rc = vc_carve_download_sparse(h_, sp.flags.data(), nb, sp.listed.data(), sp.words.data(), cap, &n);
+            if (rc == VC_ERR_CAPACITY && n > cap && attempt == 0) {  // more listed bricks than guessed: the volumes are complete on the device,
+                cap = n;                                              // ask again with room (a reset + second carve: rare, and still exact)
+                check(vc_reset(h_));
+                continue;
+            }
+            check(rc);
+            break;
+        }
+        sp.listed.resize(n);
+        sp.words.resize(n * 128);
     }
     void fastCarve(int mode = VC_EXACT) { check(vc_fast_carve(h_, mode)); }
     void color(int mode) { check(vc_color(h_, mode)); }
@@ -163,6 +196,58 @@ void applyCarve(ModelT& model, const std::vector<uint32_t>& occ, const std::vect
                 const size_t w = ((size_t)z * Y + y) * Wx + (x >> 5);
                 if (!((occ[w] >> (x & 31)) & 1u)) model.set(x, y, z, zero);
                 if ((seen[w] >> (x & 31)) & 1u) model.see(x, y, z);
+            }
+}
+
+// sparse result of a fresh carve -> the reference Model, brick by brick: a carved brick clears and sees all its voxels, a seen
+// brick sees them, an untouched one costs nothing, a listed one is applied bit by bit
+template <class ModelT>
+void applyCarveSparse(ModelT& model, const SparseCarve& sp, int z_begin = 0) {
+    const Vec4Of<ModelT> zero(0.f, 0.f, 0.f, 0.f);
+    std::vector<int64_t> slot((size_t)sp.nbx * sp.nby * sp.nbz, -1);
+    for (size_t i = 0; i < sp.listed.size(); i++) slot[sp.listed[i]] = (int64_t)i;
+    for (uint32_t bz = 0; bz < sp.nbz; bz++)
+        for (uint32_t by = 0; by < sp.nby; by++)
+            for (uint32_t bx = 0; bx < sp.nbx; bx++) {
+                const size_t b = ((size_t)bz * sp.nby + by) * sp.nbx + bx;
+                const uint8_t f = sp.flags[b];
+                if (!(f & (1 | 2 | 8))) continue;
+                const int x0 = (int)bx * 32, x1 = std::min(x0 + 32, sp.X), y0 = (int)by * 8, y1 = std::min(y0 + 8, sp.Y), z0 = (int)bz * 8, z1 = std::min(z0 + 8, sp.nz);
+                const uint32_t* w = (f & 8) ? &sp.words[(size_t)slot[b] * 128] : nullptr;
+                for (int z = z0; z < z1; z++)
+                    for (int y = y0; y < y1; y++) {
+                        const uint32_t o = w ? w[(z - z0) * 8 + (y - y0)] : ((f & 1) ? 0u : 0xffffffffu);
+                        const uint32_t sn = w ? w[64 + (z - z0) * 8 + (y - y0)] : ((f & 2) ? 0xffffffffu : 0u);
+                        for (int x = x0; x < x1; x++) {
+                            if (!((o >> (x & 31)) & 1u)) model.set(x, y, z_begin + z, zero);
+                            if ((sn >> (x & 31)) & 1u) model.see(x, y, z_begin + z);
+                        }
+                    }
+            }
+}
+
+// sparse result -> the plain bit volumes (what carveDownload delivers)
+inline void expandSparse(const SparseCarve& sp, std::vector<uint32_t>& occ, std::vector<uint32_t>& seen) {
+    const int Wx = (sp.X + 31) / 32;
+    occ.assign((size_t)sp.nz * sp.Y * Wx, 0u);
+    seen.assign(occ.size(), 0u);
+    std::vector<int64_t> slot((size_t)sp.nbx * sp.nby * sp.nbz, -1);
+    for (size_t i = 0; i < sp.listed.size(); i++) slot[sp.listed[i]] = (int64_t)i;
+    for (uint32_t bz = 0; bz < sp.nbz; bz++)
+        for (uint32_t by = 0; by < sp.nby; by++)
+            for (uint32_t bx = 0; bx < sp.nbx; bx++) {
+                const size_t b = ((size_t)bz * sp.nby + by) * sp.nbx + bx;
+                const uint8_t f = sp.flags[b];
+                const int rem = sp.X - (int)bx * 32;
+                const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+                const uint32_t* w = (f & 8) ? &sp.words[(size_t)slot[b] * 128] : nullptr;
+                for (int z = (int)bz * 8; z < std::min((int)bz * 8 + 8, sp.nz); z++)
+                    for (int y = (int)by * 8; y < std::min((int)by * 8 + 8, sp.Y); y++) {
+                        const size_t i = ((size_t)z * sp.Y + y) * Wx + bx;
+                        const int r = (z - (int)bz * 8) * 8 + (y - (int)by * 8);
+                        occ[i] = w ? w[r] : ((f & 1) ? 0u : valid);
+                        seen[i] = w ? w[64 + r] : ((f & 2) ? valid : 0u);
+                    }
             }
 }
 
@@ -254,16 +339,18 @@ void carve(const ViewCache& views, ModelT& model, bool intermediateMeshes = fals
         }
         occ = e.occupied();
         seen = e.seen();
-    } else {
-        e.carveDownload(occ, seen);
+        detail::applyCarve(model, occ, seen);
+    } else {  // the common case: sparse download (a few % of the bytes), applied brick by brick
+        SparseCarve sp;
+        e.carveDownloadSparse(sp);
+        detail::applyCarveSparse(model, sp);
     }
-    detail::applyCarve(model, occ, seen);
     std::cout << "LOG - VC: carving complete." << std::endl;
 }
 
 // carve() on several GPUs of this host: the grid is cut into balanced z-slabs (vc_plan_slabs), one engine and one host
-// thread per device, every engine sees all views; each slab goes straight from its GPU into its place in the whole-grid host
-// words (one PCIe link per GPU, no device-to-device traffic: a host Model needs no all-gather).  Same Model as carve().
+// thread per device, every engine sees all views; each slab comes back from its GPU in sparse form (one PCIe link per GPU, no
+// device-to-device traffic: a host Model needs no all-gather) and is applied to the Model.  Same Model as carve().
 template <class ModelT>
 void carveOnDevices(const ViewCache& views, ModelT& model, const std::vector<int>& devices) {
     if (devices.size() <= 1) {
@@ -273,8 +360,7 @@ void carveOnDevices(const ViewCache& views, ModelT& model, const std::vector<int
     std::cout << "LOG - VC: starting carving process (version 1)." << std::endl;
     const int X = model.getX(), Y = model.getY(), Z = model.getZ(), n = (int)std::min<size_t>(devices.size(), (size_t)Z);
     const float size = model.getSize();
-    const size_t plane = (size_t)Y * ((X + 31) / 32);
-    std::vector<uint32_t> occ(plane * Z), seen(plane * Z);
+    std::vector<SparseCarve> parts((size_t)n);
     std::vector<int32_t> bounds;
     {
         Engine planner(X, Y, Z, size, 0, -1, devices[0]);
@@ -288,7 +374,7 @@ void carveOnDevices(const ViewCache& views, ModelT& model, const std::vector<int
             try {
                 Engine e(X, Y, Z, size, bounds[r], bounds[r + 1], devices[r]);
                 e.setViews(views, false);
-                e.carveDownloadInto(occ.data() + plane * bounds[r], seen.data() + plane * bounds[r]);
+                e.carveDownloadSparse(parts[r]);
             } catch (const std::exception& ex) {
                 errors[r] = ex.what();
             }
@@ -296,7 +382,7 @@ void carveOnDevices(const ViewCache& views, ModelT& model, const std::vector<int
     for (auto& t : threads) t.join();
     for (const auto& m : errors)
         if (!m.empty()) throw Error(VC_ERR_CUDA, m);
-    detail::applyCarve(model, occ, seen);
+    for (int r = 0; r < n; r++) detail::applyCarveSparse(model, parts[r], bounds[r]);  // one thread: Model::seen is a vector<bool>
     std::cout << "LOG - VC: carving complete." << std::endl;
 }
 

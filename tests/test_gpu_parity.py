@@ -879,3 +879,40 @@ def test_nccl_two_ranks_halos_gather_bitwise(A, tmp_path):
         v = json.load(open(out / f"rank{rank}.json"))
         assert v["ok"], v
         assert v["world"] == 2 and v["nccl_version"] > 0
+
+
+@pytest.mark.parametrize("dims,slab", [((64, 64, 64), None), ((100, 37, 45), None), ((33, 9, 10), None), ((130, 70, 50), (13, 41)), ((5, 3, 2), None)])
+def test_sparse_download_expands_to_the_dense_result(A, oracle, dims, slab):
+    """vc_carve_download_sparse: flag byte per brick + words of the listed bricks only; expanded on the host it is the same
+    pair of volumes carve + download delivers (and the oracle computes) - on ragged grids, slabs, grids smaller than a brick"""
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = dims
+    z0, z1 = slab if slab else (0, Z)
+    w = Workload(max(dims), 8, 256, 192, seed=11, dims=dims)
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z1)
+    with A.VoxelEngine(X, Y, Z, w.s, z_begin=z0, z_end=z1) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        flags, listed, words = e.carve_download_sparse()
+        occ, seen = e.expand_sparse(flags, listed, words)
+        assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+        assert np.array_equal(e.download_occupied(), ro)          # the device volumes are complete too
+        assert len(listed) == int(((flags & 8) != 0).sum())
+        assert len(set(listed.tolist())) == len(listed)
+        assert ((flags.reshape(-1)[listed] & 8) != 0).all()
+        # sparse bytes vs dense bytes
+        assert flags.nbytes + listed.nbytes + words.nbytes <= 2 * occ.nbytes + flags.nbytes + 4096
+        # room for one listed brick too few: VC_ERR_CAPACITY, nothing half-written is reported as a result
+        if len(listed) > 1:
+            import ctypes as C
+            n = C.c_uint64()
+            small_l, small_w = np.empty(len(listed) - 1, np.uint32), np.empty((len(listed) - 1) * 128, np.uint32)
+            e.reset()
+            rc = e._lib.vc_carve_download_sparse(e._h, C.c_void_p(flags.ctypes.data), flags.size, C.c_void_p(small_l.ctypes.data), C.c_void_p(small_w.ctypes.data),
+                                                 len(listed) - 1, C.byref(n))
+            assert rc == A._lib.VC_ERR_CAPACITY and n.value == len(listed)
+        # not a fresh carve: the sparse form cannot describe it
+        import ctypes as C
+        n = C.c_uint64()
+        rc = e._lib.vc_carve_download_sparse(e._h, C.c_void_p(flags.ctypes.data), flags.size, C.c_void_p(listed.ctypes.data), C.c_void_p(words.ctypes.data), len(listed), C.byref(n))
+        assert rc == A._lib.VC_ERR_STATE
