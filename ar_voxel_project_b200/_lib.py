@@ -37,6 +37,7 @@ SIGNATURES = {
     "vc_api_version": (C.c_int, []),
     "vc_set_stream": (C.c_int, [_P, _P]),
     "vc_synchronize": (C.c_int, [_P]),
+    "vc_set_profiling": (C.c_int, [_P, C.c_int32]),
     "vc_set_views": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vc_set_masks": (C.c_int, [_P, _P, C.c_int32]),
     "vc_set_images": (C.c_int, [_P, _P]),

@@ -37,6 +37,20 @@ static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n,
                                     double** ir_buf = nullptr, size_t* ir_count = nullptr);
 }
 
+// Everything the launches of one VC_EXACT carve depend on: when it is unchanged, the captured CUDA graph of the last such
+// carve (memset of the counters + the three kernels + the mid-point event) is launched again - one driver call instead of
+// five, and no host-side launch gaps between kernels that run for tens of microseconds each.
+struct CarveGraphKey {
+    VcCarveParams p;
+    const void* ptrs[10];
+    int fresh, sm_count, nbx_pad;
+};
+struct CarveGraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    CarveGraphKey key;
+    bool valid = false;
+};
+
 struct vc_engine {
     vc_grid_desc g{};
     int Wx = 0, nz = 0;
@@ -70,6 +84,7 @@ struct vc_engine {
     bool have_M = false;
     uint32_t* d_mask = nullptr;
     VcViewFilter* d_filt = nullptr;      // global copy of c_filt for lane-divergent reads (sub-brick classification)
+    VcViewConst* d_view64 = nullptr;     // global copy of c_view for lane-divergent reads (deferred exact evaluations)
     uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
     uint32_t* d_sat_tmp = nullptr;       // V x H x Ww word-column prefixes used while building d_sat
     uint8_t* d_bgr_tmp = nullptr;        // staging for 8UC3 masks (grow-only)
@@ -79,6 +94,10 @@ struct vc_engine {
     uint8_t* d_brick_flags = nullptr;    // VC_BRICK_* flags per brick
     uint8_t* d_super_flags = nullptr;    // ... per super-brick
     unsigned int* d_super_list = nullptr;
+    CarveGraphSlot graph_slot[2];        // [fresh] cached graphs of a whole-range VC_EXACT carve
+    int use_graphs = -1;                 // -1: not decided yet (environment variable VOXCARVE_NO_GRAPH=1 switches them off)
+    bool profiling = false;              // vc_set_profiling: plain launches with an event between classification and per-voxel kernel
+    int resident_blocks = 0;             // of vc_carve_bricks per SM (occupancy query, once)
     bool reset_pending = false;          // vc_reset not yet materialised (a VC_EXACT carve folds it into its fill pass)
     bool carved_implies_seen = true;     // invariant of every state the engine produces; uploaded volumes may break it (vc_upload_volumes)
     // grow-only scratch shared by vc_fast_carve (flood volume), vc_mc_mesh (column counts), raw uploads and the
@@ -233,6 +252,20 @@ void set_mask_window(vc_engine* e, bool on) {
     }
 }
 
+// launch with programmatic stream serialization: the kernel may begin while the previous kernel of the stream drains (it
+// synchronises itself with vc_pdl_wait before touching that kernel's results)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int K>
 int launch_carve(vc_engine* e, int mode, const VcCarveParams& p, bool count) {
     const long long blocks = (long long)p.G * p.YB * e->nz;
@@ -341,6 +374,7 @@ int vc_create(const vc_grid_desc* grid, vc_engine** out) {
     VC_CREATE_CUDA(cudaMalloc(&e->d_scalars, 16 * sizeof(unsigned long long)));
     VC_CREATE_CUDA(cudaMalloc(&e->d_hist, 257 * sizeof(unsigned long long)));  // [256] = task counter of vc_mc_classify_kernel
     VC_CREATE_CUDA(cudaMalloc(&e->d_filt, VC_MAX_VIEWS * sizeof(VcViewFilter)));
+    VC_CREATE_CUDA(cudaMalloc(&e->d_view64, VC_MAX_VIEWS * sizeof(VcViewConst)));
 #undef VC_CREATE_CUDA
     *out = e;
     int rc = vc_reset(e);
@@ -355,11 +389,12 @@ void vc_destroy(vc_engine* e) {
     cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
     cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_block_sums);
-    cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt);
+    cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt); cudaFree(e->d_view64);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
     cudaFree(e->d_sparse_idx); cudaFree(e->d_sparse_words);
     cudaFree(e->d_scratch); cudaFree(e->d_undist_ir); cudaFree(e->d_occ_full_own); cudaFree(e->d_seen_full_own); cudaFree(e->d_reduce);
     if (e->comm) vc_comm_destroy(e);
+    for (CarveGraphSlot& gs : e->graph_slot) if (gs.exec) cudaGraphExecDestroy(gs.exec);
     if (e->ev_halo) cudaEventDestroy(e->ev_halo);
     free_color(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -381,6 +416,12 @@ int vc_set_stream(vc_engine* e, void* cuda_stream) {
     if (bind_device(e)) return VC_ERR_CUDA;
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return VC_OK;
+}
+
+int vc_set_profiling(vc_engine* e, int32_t on) {
+    if (!e) return VC_ERR_ARG;
+    e->profiling = on != 0;
     return VC_OK;
 }
 
@@ -424,6 +465,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     e->have_M = M != nullptr;
     vc_filter_constants(e);
     VC_CUDA(e, cudaMemcpyAsync(e->d_filt, e->h_filt.data(), sizeof(VcViewFilter) * V, cudaMemcpyHostToDevice, e->stream));  // h_filt lives until the next vc_set_views, which synchronises first
+    VC_CUDA(e, cudaMemcpyAsync(e->d_view64, e->h_view.data(), sizeof(VcViewConst) * V, cudaMemcpyHostToDevice, e->stream));
     e->views_version++;
     return VC_OK;
 }
@@ -659,6 +701,9 @@ static int ensure_brick_buffers(vc_engine* e) {
     if (n_bricks > 0x7fffffffLL) return fail(e, VC_ERR_ARG, "slab too large for one launch (%lld bricks)", n_bricks);
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER + 1;
     const long long n_super = (long long)sbx * sby * sbz;
+    if (e->resident_blocks < 1) {  // persistent grid of vc_carve_bricks: as many blocks of 8 warps as are resident at once
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resident_blocks, vc_carve_bricks<false>, 256, 0) != cudaSuccess || e->resident_blocks < 1) { cudaGetLastError(); e->resident_blocks = 2; }
+    }
     if (e->d_bricks) return VC_OK;
     VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
     VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
@@ -707,12 +752,18 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = p.v0; bp.v1 = p.v1; bp.s = e->g.voxel_size;
     VcBrickParams sp = bp;  // level 1: super-bricks into the dense array
     sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
-    vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super + VC_CLS_L1_CH - 1) / VC_CLS_L1_CH), 256, 0, e->stream>>>(sp);  // VC_CLS_L1_CH super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-    vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
-    if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));
-    int resident = 0;  // persistent grid: as many blocks of 8 warps as are resident at once
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, vc_carve_bricks<false>, 256, 0) != cudaSuccess || resident < 1) { cudaGetLastError(); resident = 2; }
+    const bool pdl = !record_mid;  // an event record between two kernels would keep them from overlapping anyway
+    {   // level 0: the blocks walk the list of undecided super-bricks (length known on the device only)
+        const long long l0_grid = std::min<long long>(n_super, 8LL * e->sm_count);
+        VC_CUDA(e, launch_pdl(vc_brick_classify_kernel<0>, dim3((unsigned)l0_grid), dim3(VC_CLS_L0_THREADS), e->stream, pdl, bp));
+    }
+    if (record_mid) VC_CUDA(e, cudaEventRecord(e->evm, e->stream));  // (profiling / counting runs only: it sits between two kernels that otherwise overlap their launch)
+    if (e->resident_blocks < 1) {  // persistent grid: as many blocks of 8 warps as are resident at once
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resident_blocks, vc_carve_bricks<false>, 256, 0) != cudaSuccess || e->resident_blocks < 1) { cudaGetLastError(); e->resident_blocks = 2; }
+    }
+    const int resident = e->resident_blocks;
     const unsigned pgrid = (unsigned)e->sm_count * (unsigned)resident;
     // Fill pass (volume words implied by the brick flags).  Fresh carve, rows of whole quads: the first blocks of the persistent
     // kernel do it themselves, skipping the listed bricks, whose words the work items own.  Otherwise it runs first, in
@@ -740,8 +791,16 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
         vc_fill_kernel<<<dim3((e->g.Y + 7) / 8, p.nz, (e->Wx + 31) / 32), dim3(32, 8), 0, e->stream>>>(
             p.occ, p.seen, e->d_brick_flags, e->d_super_flags, e->g.X, e->g.Y, e->Wx, nby, sbx, sby, fresh ? 1 : 0, 0);
     }
-    if (count) vc_carve_bricks<true><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work + 1, (unsigned)n_bricks, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt, fp);
-    else vc_carve_bricks<false><<<pgrid, 256, 0, e->stream>>>(p, e->d_bricks, d_nlist, d_work + 1, (unsigned)n_bricks, d_work, nbx, nby, e->d_sat, fresh ? 1 : 0, e->d_filt, fp);
+    // (the fill kernels of a non-fresh carve sit between the classification and this one: then it is they that it would overlap,
+    // and its vc_pdl_wait still orders it after everything before it in the stream)
+    const bool pdl_cb = pdl && fresh && quads;
+    const VcBrickState* list_c = e->d_bricks;
+    const unsigned int *n_front_c = d_nlist, *n_back_c = d_work + 1;
+    const uint32_t* sat_c = e->d_sat;
+    const VcViewFilter* filt_c = e->d_filt;
+    const VcViewConst* view_c = e->d_view64;
+    if (count) VC_CUDA(e, launch_pdl(vc_carve_bricks<true>, dim3(pgrid), dim3(256), e->stream, pdl_cb, p, list_c, n_front_c, n_back_c, (unsigned)n_bricks, d_work, nbx, nby, sat_c, fresh ? 1 : 0, filt_c, view_c, fp));
+    else VC_CUDA(e, launch_pdl(vc_carve_bricks<false>, dim3(pgrid), dim3(256), e->stream, pdl_cb, p, list_c, n_front_c, n_back_c, (unsigned)n_bricks, d_work, nbx, nby, sat_c, fresh ? 1 : 0, filt_c, view_c, fp));
     VC_CUDA(e, cudaGetLastError());
     e->stats.carve_launches += (fresh && quads) ? 3 : 4;
     if (n_bricks_out) *n_bricks_out += (uint64_t)n_bricks;
@@ -797,8 +856,47 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
     e->stats.bricks_total = 0;
     e->stats.bricks_listed = 0;
     if (mode == VC_EXACT) {
-        rc = carve_exact_range(e, p, 0, e->nz, count_executed != 0, e->reset_pending, true, &e->stats.bricks_total);
-        if (rc) return rc;
+        if (e->use_graphs < 0) { const char* ng = getenv("VOXCARVE_NO_GRAPH"); e->use_graphs = (ng && atoi(ng) != 0) ? 0 : 1; }
+        const bool fresh = e->reset_pending;
+        bool launched = false;
+        if (e->use_graphs && !e->profiling && !count_executed && view_begin == 0 && view_end == e->V) {
+            CarveGraphKey k;
+            memset(&k, 0, sizeof k);  // padding bytes too: the key is compared with memcmp
+            k.p = p;
+            const void* ptrs[10] = {e->d_bricks, e->d_super, e->d_brick_flags, e->d_super_flags, e->d_super_list, e->d_sat, e->d_filt, e->d_view64, e->d_scalars, e->evm};
+            memcpy(k.ptrs, ptrs, sizeof ptrs);
+            k.fresh = fresh ? 1 : 0; k.sm_count = e->sm_count; k.nbx_pad = 0;
+            CarveGraphSlot& gs = e->graph_slot[fresh ? 1 : 0];
+            bool captured_now = false;
+            if (!gs.valid || memcmp(&gs.key, &k, sizeof k) != 0) {
+                captured_now = true;
+                if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+                gs.valid = false;
+                cudaGraph_t graph = nullptr;
+                VC_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+                uint64_t nb_dummy = 0;
+                rc = carve_exact_range(e, p, 0, e->nz, false, fresh, false, &nb_dummy);
+                const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);  // always end the capture, also after a failed launch
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(e, VC_ERR_CUDA, "vc_carve: stream capture failed: %s", cudaGetErrorString(ce));
+                const cudaError_t ci = cudaGraphInstantiate(&gs.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ci != cudaSuccess) { gs.exec = nullptr; return fail(e, VC_ERR_CUDA, "vc_carve: cudaGraphInstantiate failed: %s", cudaGetErrorString(ci)); }
+                gs.key = k;
+                gs.valid = true;
+            }
+            VC_CUDA(e, cudaGraphLaunch(gs.exec, e->stream));
+            if (!captured_now) e->stats.carve_launches += (fresh && e->Wx % 4 == 0) ? 3 : 4;  // the capture counted its own
+            const int nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
+            e->stats.bricks_total = (uint64_t)e->Wx * nby * nbz;
+            e->have_mid = false;
+            launched = true;
+        }
+        if (!launched) {
+            e->have_mid = e->profiling || count_executed != 0;
+            rc = carve_exact_range(e, p, 0, e->nz, count_executed != 0, fresh, e->have_mid, &e->stats.bricks_total);
+            if (rc) return rc;
+        }
         e->reset_pending = false;
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
@@ -1042,9 +1140,12 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.W = e->W; bp.H = e->H; bp.v0 = 0; bp.v1 = e->V; bp.s = e->g.voxel_size;
     VcBrickParams sp = bp;
     sp.dense = e->d_super; sp.nbx = sbx; sp.nby = sby; sp.nbz = sbz;
-    vc_brick_classify_kernel<1><<<(unsigned)((n_super + 15) / 16), 256, 0, e->stream>>>(sp);  // 16 super-bricks per block
+    vc_brick_classify_kernel<1><<<(unsigned)((n_super + VC_CLS_L1_CH - 1) / VC_CLS_L1_CH), 256, 0, e->stream>>>(sp);  // VC_CLS_L1_CH super-bricks per block
     bp.dense = e->d_super; bp.pbx = sbx; bp.pby = sby;
-    vc_brick_classify_kernel<0><<<(unsigned)n_super, 256, 0, e->stream>>>(bp);  // one block per listed super-brick; blocks beyond the list exit at once
+    {   // level 0: the blocks walk the list of undecided super-bricks (length known on the device only)
+        const long long l0_grid = std::min<long long>(n_super, 8LL * e->sm_count);
+        vc_brick_classify_kernel<0><<<(unsigned)l0_grid, VC_CLS_L0_THREADS, 0, e->stream>>>(bp);
+    }
     unsigned int counts[4] = {0, 0, 0, 0};  // front length, super-list length, (work counter), back length
     VC_CUDA(e, cudaMemcpyAsync(counts, d_nlist, sizeof counts, cudaMemcpyDeviceToHost, e->stream));
     VC_CUDA(e, cudaStreamSynchronize(e->stream));

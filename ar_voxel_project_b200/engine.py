@@ -99,6 +99,10 @@ class VoxelEngine:
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.vc_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
+    def set_profiling(self, on=True):
+        """plain launches + an event between classification and per-voxel kernel (stats()['last_classify_ms']) instead of one CUDA graph"""
+        self._check(self._lib.vc_set_profiling(self._h, int(bool(on))))
+
     def synchronize(self):
         self._check(self._lib.vc_synchronize(self._h))
 

@@ -102,6 +102,11 @@ VC_EXPORT int vc_api_version(void);
 /* run all work of this engine on a caller stream (cudaStream_t as void*; NULL = engine's own) */
 VC_EXPORT int vc_set_stream(vc_engine* e, void* cuda_stream);
 VC_EXPORT int vc_synchronize(vc_engine* e);
+/* Profiling mode (off by default).  Off: a whole-range VC_EXACT carve is launched as ONE cached CUDA graph (counter reset + the
+ * two classification kernels + the per-voxel kernel; re-captured whenever grid, slab, views, buffers or stream arguments
+ * change; VOXCARVE_NO_GRAPH=1 in the environment disables it) and vc_stats.last_classify_ms stays 0.  On: plain launches with
+ * an event between classification and per-voxel kernel, so that vc_stats splits the carve time and ncu sees every launch. */
+VC_EXPORT int vc_set_profiling(vc_engine* e, int32_t on);
 
 /* ---- inputs ---------------------------------------------------------------------- */
 /* Per-view camera data, cached once per dataset (replaces the per-call

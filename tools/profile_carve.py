@@ -21,6 +21,7 @@ w = Workload(**CONFIGS[a.config])
 with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
     e.set_views(w.P, w.W, w.H, w.M)
     e.set_masks_bits(w.mask_bits)
+    e.set_profiling(True)   # plain launches: ncu sees every kernel, stats() splits classification from the per-voxel kernel
     for _ in range(a.reps):
         e.reset()
         e.carve(a.mode)
