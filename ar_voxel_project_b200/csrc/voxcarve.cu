@@ -85,7 +85,7 @@ struct vc_engine {
     uint32_t* d_mask = nullptr;
     VcViewFilter* d_filt = nullptr;      // global copy of c_filt for lane-divergent reads (sub-brick classification)
     VcViewConst* d_view64 = nullptr;     // global copy of c_view for lane-divergent reads (deferred exact evaluations)
-    uint32_t* d_sat = nullptr;           // summed-area tables of the background bits, V x (H+1) x (W+1)
+    vc_sat_t* d_sat = nullptr;           // summed-area tables of the background bits modulo 2^16, V x (H+1) x (W+1)
     uint32_t* d_sat_tmp = nullptr;       // V x H x Ww word-column prefixes used while building d_sat
     uint8_t* d_bgr_tmp = nullptr;        // staging for 8UC3 masks (grow-only)
     size_t bgr_tmp_bytes = 0;
@@ -506,7 +506,7 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
     }
     // summed-area tables for the brick classifier of VC_EXACT
     const size_t sat_words = (size_t)e->V * (e->H + 1) * (e->W + 1);
-    if (!e->d_sat) VC_CUDA(e, cudaMalloc(&e->d_sat, sat_words * 4));
+    if (!e->d_sat) VC_CUDA(e, cudaMalloc(&e->d_sat, sat_words * sizeof(vc_sat_t)));
     if (!e->d_sat_tmp) VC_CUDA(e, cudaMalloc(&e->d_sat_tmp, e->mask_bytes));
     {
         const long long n_rows = (long long)e->V * e->H;
@@ -796,7 +796,7 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     const bool pdl_cb = pdl && fresh && quads;
     const VcBrickState* list_c = e->d_bricks;
     const unsigned int *n_front_c = d_nlist, *n_back_c = d_work + 1;
-    const uint32_t* sat_c = e->d_sat;
+    const vc_sat_t* sat_c = e->d_sat;
     const VcViewFilter* filt_c = e->d_filt;
     const VcViewConst* view_c = e->d_view64;
     if (count) VC_CUDA(e, launch_pdl(vc_carve_bricks<true>, dim3(pgrid), dim3(256), e->stream, pdl_cb, p, list_c, n_front_c, n_back_c, (unsigned)n_bricks, d_work, nbx, nby, sat_c, fresh ? 1 : 0, filt_c, view_c, fp));

@@ -916,3 +916,36 @@ def test_sparse_download_expands_to_the_dense_result(A, oracle, dims, slab):
         n = C.c_uint64()
         rc = e._lib.vc_carve_download_sparse(e._h, C.c_void_p(flags.ctypes.data), flags.size, C.c_void_p(listed.ctypes.data), C.c_void_p(words.ctypes.data), len(listed), C.byref(n))
         assert rc == A._lib.VC_ERR_STATE
+
+
+def test_rectangles_beyond_the_16_bit_table_are_left_to_the_children(A, oracle):
+    """the summed-area tables are kept modulo 2^16: a (super-)brick whose pixel rectangle holds 2^16 pixels or more cannot be
+    counted and must stay undecided - close cameras on a large image make whole super-bricks project to > 256 x 256 pixels;
+    the volumes still equal the oracle's and the flat kernel's"""
+    from ar_voxel_project_b200.synth import pack_bits
+    X, Y, Z, W, H = 256, 64, 64, 1024, 768
+    s = np.float32(0.004)
+    rng = np.random.default_rng(21)
+    ext = np.array([Y * s, X * s, Z * s])
+    centre = np.array([ext[0] / 2, ext[1] / 2, -ext[2] / 2])
+    P = []
+    for v in range(6):
+        pos = centre + rng.normal(size=3) * ext.max() * (0.55 if v < 4 else 2.0)   # four cameras right at the grid, two further away
+        zc = centre + (rng.random(3) - 0.5) * ext * 0.3 - pos
+        zc /= np.linalg.norm(zc)
+        xc = np.cross(zc, rng.normal(size=3))
+        xc /= np.linalg.norm(xc)
+        R = np.stack([xc, np.cross(zc, xc), zc])
+        f = W * 1.4
+        K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
+        M = np.concatenate([R, (-R @ pos)[:, None]], axis=1).astype(np.float32)
+        P.append(oracle.gemm3x3_3x4(K.astype(np.float32), M))
+    P = np.stack(P)
+    yy, xx = np.mgrid[0:H, 0:W]
+    bg = np.stack([((xx - W * (0.3 + 0.1 * v)) ** 2 + (yy - H / 2) ** 2) > (0.35 * H) ** 2 for v in range(6)])
+    bg[1] = True      # one view that is background everywhere: carves whatever it sees, in rectangles of any size
+    bg[2] = False     # and one that is foreground everywhere
+    bits = pack_bits(bg)
+    ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits, nthreads=0)
+    occ, seen, st = _carve(A, X, Y, Z, s, P, W, H, bits=bits, count=True)
+    assert np.array_equal(occ, ro) and np.array_equal(seen, rs)

@@ -12,13 +12,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C4")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--slab", default=None, help="z0,z1: carve only this z-slab (what one rank of an N-GPU run does)")
 ap.add_argument("--lib", default=None, help="experiment variant of libvoxcarve.so (see build.build(out=...))")
 a = ap.parse_args()
 if a.lib:
     import ar_voxel_project_b200._lib as L
     L.LIB_PATH = os.path.abspath(a.lib)
 w = Workload(**CONFIGS[a.config])
-with A.VoxelEngine(w.X, w.Y, w.Z, w.s) as e:
+z0, z1 = [int(x) for x in a.slab.split(",")] if a.slab else (0, w.Z)
+with A.VoxelEngine(w.X, w.Y, w.Z, w.s, z_begin=z0, z_end=z1) as e:
     e.set_views(w.P, w.W, w.H, w.M)
     e.set_masks_bits(w.mask_bits)
     e.set_profiling(True)   # plain launches: ncu sees every kernel, stats() splits classification from the per-voxel kernel
