@@ -949,3 +949,26 @@ def test_rectangles_beyond_the_16_bit_table_are_left_to_the_children(A, oracle):
     ro, rs = oracle.carve(X, Y, Z, s, P, W, H, mask_bits=bits, nthreads=0)
     occ, seen, st = _carve(A, X, Y, Z, s, P, W, H, bits=bits, count=True)
     assert np.array_equal(occ, ro) and np.array_equal(seen, rs)
+
+
+def test_masks_from_page_locked_memory_without_a_sync(A, oracle):
+    """page-locked host masks (bits or 8UC3) uploaded asynchronously with the carve enqueued right behind them (the end-to-end
+    path of bench.py): same device masks, same carve as the synchronous path"""
+    import torch
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 80, 50, 40
+    w = Workload(80, 11, 300, 220, seed=13, dims=(X, Y, Z))   # 11 views: groups of 2, 3, 3, 3
+    ro, rs = oracle.carve(X, Y, Z, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits)
+    bits_p = torch.from_numpy(w.mask_bits.view(np.int32).copy()).pin_memory()
+    bgr_p = torch.from_numpy(w.mask_bgr()).pin_memory()
+    with A.VoxelEngine(X, Y, Z, w.s) as e:
+        e.set_views(w.P, w.W, w.H)
+        for kind in ("bits", "bgr", "bits"):
+            if kind == "bits":
+                e.set_masks_bits_async(bits_p)
+            else:
+                e.set_masks_bgr(bgr_p, sync=False)
+            e.reset()
+            e.carve()          # enqueued right behind the uploads
+            assert np.array_equal(e.download_occupied(), ro) and np.array_equal(e.download_seen(), rs), kind
+            assert np.array_equal(e.download_masks(), w.mask_bits), kind
