@@ -99,6 +99,7 @@ struct vc_engine {
     bool profiling = false;              // vc_set_profiling: plain launches with an event between classification and per-voxel kernel
     int resident_blocks = 0;             // of vc_carve_bricks per SM (occupancy query, once)
     bool reset_pending = false;          // vc_reset not yet materialised (a VC_EXACT carve folds it into its fill pass)
+    bool flags_valid = false;            // the brick / super-brick flags describe the volumes as they are (after a fresh whole-range VC_EXACT carve)
     bool carved_implies_seen = true;     // invariant of every state the engine produces; uploaded volumes may break it (vc_upload_volumes)
     // grow-only scratch shared by vc_fast_carve (flood volume), vc_mc_mesh (column counts), raw uploads and the
     // carved-but-unseen path of vc_carve: none of them runs concurrently with another on this engine's stream
@@ -697,6 +698,7 @@ int vc_undistort_bgr(int32_t device, int32_t n, int32_t W, int32_t H, const uint
 int vc_reset(vc_engine* e) {
     if (!e) return VC_ERR_ARG;
     e->reset_pending = true;  // lazy: vc_carve(VC_EXACT) folds it into its coalesced fill pass
+    e->flags_valid = false;
     e->carved_implies_seen = true;
     e->gathered = false;
     e->halo_lo = e->halo_hi = false;
@@ -909,9 +911,11 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
             if (rc) return rc;
         }
         e->reset_pending = false;
+        e->flags_valid = fresh && view_begin == 0 && view_end == e->V;  // the flags of this call say everything about the volumes
     } else {
         rc = launch_carve<4>(e, mode == VC_EXACT_FLAT ? VC_EXACT : mode, p, count_executed != 0);
         if (rc) return rc;
+        e->flags_valid = false;
     }
     if (d_saved_occ) {
         vc_unseen_end_kernel<<<(unsigned)((e->slab_words + 255) / 256), 256, 0, e->stream>>>(e->occ_slab(), d_saved_occ, e->slab_words);
@@ -993,6 +997,7 @@ int vc_carve_download(vc_engine* e, int32_t mode, uint32_t* occupied, uint32_t* 
         VC_CUDA(e, cudaMemcpyAsync(seen + off, e->seen_slab() + off, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
     }
     e->reset_pending = false;
+    e->flags_valid = false;  // the flag arrays were re-used chunk by chunk
     VC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     rc = constants_used(e);
     if (rc) return rc;
@@ -1101,6 +1106,7 @@ int vc_fast_carve(vc_engine* e, int32_t mode) {
         VC_CUDA(e, cudaStreamSynchronize(e->stream));
         if (!h) break;
     }
+    e->flags_valid = false;  // the flood rewrites the volumes
     vc_flood_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(F, occ, seen, X, Y, Z, Wx);
     VC_CUDA(e, cudaGetLastError());
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1138,6 +1144,7 @@ int vc_plan_slabs(vc_engine* e, int32_t n_parts, int32_t* z_bounds) {
     if (nbz < n_parts) return VC_OK;  // fewer brick layers than parts: keep the uniform split
     rc = ensure_brick_buffers(e);
     if (rc) return rc;
+    e->flags_valid = false;
     // both classification levels of VC_EXACT over the whole range, no volumes touched
     const int sbx = (nbx + VC_SUPER - 1) / VC_SUPER, sby = (nby + VC_SUPER - 1) / VC_SUPER, sbz = (nbz + VC_SUPER - 1) / VC_SUPER;
     const long long n_super = (long long)sbx * sby * sbz;
@@ -1227,6 +1234,7 @@ int vc_upload_volumes(vc_engine* e, const uint32_t* occupied, const uint32_t* se
     if (bind_device(e)) return VC_ERR_CUDA;
     if (ensure_volumes(e)) return VC_ERR_CUDA;
     e->reset_pending = false;  // overwritten entirely
+    e->flags_valid = false;
     VC_CUDA(e, cudaMemcpyAsync(e->occ_slab(), occupied, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     VC_CUDA(e, cudaMemcpyAsync(e->seen_slab(), seen, n_words * 4, cudaMemcpyHostToDevice, e->stream));
     // padding cleared; [4] counts the words that hold a voxel which is carved but unseen (the reference would still mark such a
@@ -1374,7 +1382,14 @@ int vc_mc_classify(vc_engine* e) {
     long long blocks = (n_tasks + 7) / 8;
     if (blocks > (long long)e->sm_count * 4) blocks = (long long)e->sm_count * 4;  // persistent: warps pull tasks from a counter
     (void)n;
-    vc_mc_classify_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(vol_view(e), cz_begin, n_cz, Cw, e->d_hist);
+    VcMcFlags mf{};
+    mf.enabled = (e->flags_valid && e->d_brick_flags && !e->reset_pending) ? 1 : 0;
+    if (const char* nf = getenv("VOXCARVE_MC_NO_FLAGS")) if (atoi(nf)) mf.enabled = 0;  // (measurement switch)
+    mf.brick_flags = e->d_brick_flags; mf.super_flags = e->d_super_flags;
+    mf.nby = (e->g.Y + VC_BY - 1) / VC_BY;
+    mf.pbx = (e->Wx + VC_SUPER - 1) / VC_SUPER; mf.pby = (mf.nby + VC_SUPER - 1) / VC_SUPER;
+    mf.z_begin = e->g.z_begin; mf.z_end = e->g.z_end;
+    vc_mc_classify_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(vol_view(e), cz_begin, n_cz, Cw, e->d_hist, mf);
     VC_CUDA(e, cudaGetLastError());
     e->have_mc = true;
     return VC_OK;
