@@ -448,7 +448,7 @@ int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const float* P, 
     }
     e->V = V; e->W = W; e->H = H; e->Ww = (W + 31) / 32;
     e->mask_bytes = (size_t)V * H * e->Ww * 4;
-    if ((unsigned long long)(W + 1) * (H + 1) > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: image %dx%d too large for 32-bit SAT offsets", W, H);
+    if ((unsigned long long)vc_sat_pitch(W) * (H + 1) > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: image %dx%d too large for 32-bit SAT offsets", W, H);
     if (e->mask_bytes / 4 > 0x7fffffffull) return fail(e, VC_ERR_ARG, "vc_set_views: %d views of %dx%d exceed 2^31 mask words", V, W, H);
     e->h_view.resize(V);
     e->h_cam.assign((size_t)V * 4, 0.0f);
@@ -479,7 +479,7 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
     if (format == VC_MASK_BGR8_RAW && !e->have_calib) return fail(e, VC_ERR_STATE, "vc_set_masks: raw masks need vc_set_calibration first");
     if (bind_device(e)) return VC_ERR_CUDA;
     if (!e->d_mask) VC_CUDA(e, cudaMalloc(&e->d_mask, e->mask_bytes));
-    const size_t sat_words = (size_t)e->V * (e->H + 1) * (e->W + 1);
+    const size_t sat_words = (size_t)e->V * (e->H + 1) * vc_sat_pitch(e->W);
     if (!e->d_sat) VC_CUDA(e, cudaMalloc(&e->d_sat, sat_words * sizeof(vc_sat_t)));
     if (!e->d_sat_tmp) VC_CUDA(e, cudaMalloc(&e->d_sat_tmp, e->mask_bytes));
     const size_t view_words = (size_t)e->H * e->Ww, view_bgr = (size_t)e->H * e->W * 3;
@@ -506,8 +506,7 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
             vc_pack_bgr_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(d_tmp + (size_t)v0 * view_bgr, m, e->W, e->Ww, n_rows);
         }
         vc_sat_rowprefix_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(m, t, e->Ww, n_rows);
-        vc_sat_coldown_kernel<<<(n_cols + 63) / 64, 64, 0, e->stream>>>(t, e->Ww, e->H, nv);
-        vc_sat_expand_kernel<<<(n_cols * 32 + 255) / 256, 256, 0, e->stream>>>(m, t, e->d_sat + (size_t)v0 * (e->H + 1) * (e->W + 1), e->W, e->H, e->Ww, nv);
+        vc_sat_build_kernel<<<(unsigned)n_cols, 32 * VC_SAT_WARPS, 0, e->stream>>>(m, t, e->d_sat + (size_t)v0 * (e->H + 1) * vc_sat_pitch(e->W), e->W, e->H, e->Ww, nv);
         return cudaGetLastError();
     };
     // (Uploading the views in groups on a second stream, each group's tables built while the next one travels, was measured on
