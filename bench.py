@@ -517,7 +517,13 @@ def run_ours(args):
         eng.exchange_halos()
     eng.mc_classify()
     mc_ms = timed(eng.mc_classify, 3, flush_l2=False)
-    halo_ms = timed(eng.exchange_halos, 5, flush_l2=False) if world > 1 else None
+    halo_ms = None
+    if world > 1:   # 20 exchanges inside one pair of events: a single one mostly measures how far apart the ranks arrive
+        def halos20():
+            for _ in range(20):
+                eng.exchange_halos()
+        halos20()
+        halo_ms = timed(halos20, 2, flush_l2=False) / 20.0
 
     # per-surface-voxel colouring of the carved grid (ColorReconstruction.cpp:22-70) on the same device-resident volume;
     # the 8UC3 images (V x H x W x 3, hash-coloured) are uploaded outside the timed region
@@ -537,6 +543,8 @@ def run_ours(args):
     hashes = dict(ref_hash) if ref_hash else None
     if world > 1:
         step()
+        torch.cuda.synchronize()
+        eng.gather(bounds, occupied=True, seen=True)   # first use: NCCL sets up its peer connections (seconds at 8 ranks), untimed
         torch.cuda.synchronize()
         g_occ = timed(lambda: eng.gather(bounds, occupied=True, seen=False), 3, flush_l2=False)
         g_both = timed(lambda: eng.gather(bounds, occupied=True, seen=True), 3, flush_l2=False)
