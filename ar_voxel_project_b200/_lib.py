@@ -64,6 +64,7 @@ SIGNATURES = {
     "vc_export_halo": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     "vc_import_halo": (C.c_int, [_P, C.c_int32, _P]),
     "vc_exchange_halos_peer": (C.c_int, [C.POINTER(_P), C.c_int32]),
+    "vc_gather_peer": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32]),
     "vc_comm_unique_id": (C.c_int, [_P]),
     "vc_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "vc_comm_destroy": (C.c_int, [_P]),

@@ -1786,6 +1786,48 @@ int vc_exchange_halos_peer(vc_engine** engines, int32_t n) {
     return VC_OK;
 }
 
+int vc_gather_peer(vc_engine** engines, int32_t n, int32_t what) {
+    if (!engines || n < 1 || !(what & 3) || (what & ~3)) return VC_ERR_ARG;
+    std::vector<vc_engine*> es(engines, engines + n);
+    for (vc_engine* e : es) if (!e) return VC_ERR_ARG;
+    std::sort(es.begin(), es.end(), [](const vc_engine* a, const vc_engine* b) { return a->g.z_begin < b->g.z_begin; });
+    vc_engine* e0 = es[0];
+    if (e0->g.z_begin != 0 || es[n - 1]->g.z_end != e0->g.Z) return fail(e0, VC_ERR_ARG, "vc_gather_peer: the slabs do not cover [0,%d)", e0->g.Z);
+    for (int i = 0; i < n; i++) {
+        vc_engine* e = es[i];
+        if (e->g.X != e0->g.X || e->g.Y != e0->g.Y || e->g.Z != e0->g.Z) return fail(e, VC_ERR_ARG, "vc_gather_peer: engines of different grids");
+        if (i + 1 < n && e->g.z_end != es[i + 1]->g.z_begin) return fail(e, VC_ERR_ARG, "vc_gather_peer: slabs [%d,%d) and [%d,%d) are not adjacent", e->g.z_begin, e->g.z_end, es[i + 1]->g.z_begin, es[i + 1]->g.z_end);
+        if (!e->d_occ_full) return fail(e, VC_ERR_STATE, "vc_gather_peer: every engine needs whole-grid buffers (vc_alloc_full_volumes / vc_bind_volumes)");
+        if (bind_device(e)) return VC_ERR_CUDA;
+        int rc = materialize_reset(e);
+        if (rc) return rc;
+        for (int k = 0; k < n; k++) {  // direct loads / stores over NVLink instead of staging through the host
+            if (es[k]->g.device == e->g.device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, e->g.device, es[k]->g.device) == cudaSuccess && can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(es[k]->g.device, 0);
+                if (pe != cudaSuccess) cudaGetLastError();  // already enabled
+            }
+        }
+        if (!e->ev_halo) VC_CUDA(e, cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming));
+        VC_CUDA(e, cudaEventRecord(e->ev_halo, e->stream));  // my slab is complete here
+    }
+    const size_t pw = (size_t)e0->plane_words;
+    for (int d = 0; d < n; d++) {  // every engine pulls the other slabs on its own stream, starting with its upper neighbour
+        vc_engine* dst = es[d];
+        if (bind_device(dst)) return VC_ERR_CUDA;
+        for (int k = 1; k < n; k++) {
+            vc_engine* src = es[(d + k) % n];
+            const size_t off = (size_t)src->g.z_begin * pw, bytes = (size_t)src->slab_words * 4;
+            VC_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->ev_halo, 0));
+            if (what & 1) VC_CUDA(dst, cudaMemcpyPeerAsync(dst->d_occ_full + off, dst->g.device, src->d_occ_full + off, src->g.device, bytes, dst->stream));
+            if (what & 2) VC_CUDA(dst, cudaMemcpyPeerAsync(dst->d_seen_full + off, dst->g.device, src->d_seen_full + off, src->g.device, bytes, dst->stream));
+        }
+        if (what & 1) { dst->gathered = true; dst->have_colors = false; dst->have_mc = false; }
+    }
+    return VC_OK;
+}
+
 int vc_comm_unique_id(void* unique_id_128) {
     if (!unique_id_128) return VC_ERR_ARG;
     const NcclApi* api = load_nccl();

@@ -444,6 +444,15 @@ def exchange_halos_peer(engines):
         raise VoxCarveError(rc, "; ".join(e._lib.vc_last_error(e._h).decode() for e in bad))
 
 
+def gather_peer(engines, occupied=True, seen=False):
+    """engines of THIS process whose slabs tile the grid: everyone's whole-grid buffers get all slabs (peer copies over NVLink)"""
+    lib = L.load()
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    rc = lib.vc_gather_peer(arr, len(engines), (1 if occupied else 0) | (2 if seen else 0))
+    if rc != L.VC_OK:
+        raise VoxCarveError(rc, "; ".join(e._lib.vc_last_error(e._h).decode() for e in engines if e._lib.vc_last_error(e._h)))
+
+
 def measure_peaks(device=0):
     """Measured CUDA-core FFMA / DFMA peaks (TFLOP/s) of `device` — roofline denominators for bench.py."""
     lib = L.load()

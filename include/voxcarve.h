@@ -206,6 +206,10 @@ VC_EXPORT int vc_halo_words(const vc_engine* e, uint64_t* n_words);
 VC_EXPORT int vc_export_halo(vc_engine* e, int32_t which, void** d_plane);
 VC_EXPORT int vc_import_halo(vc_engine* e, int32_t which, const void* d_plane);
 VC_EXPORT int vc_exchange_halos_peer(vc_engine** engines, int32_t n);
+/* vc_gather (below) for the engines of ONE process without NCCL: every engine pulls the other slabs into its whole-grid buffers
+ * with peer copies over NVLink on its own stream (peer access is enabled on the way), ordered after the producers by events.
+ * what: 1 = occupied, 2 = seen, 3 = both.  The slabs must tile [0, Z). */
+VC_EXPORT int vc_gather_peer(vc_engine** engines, int32_t n, int32_t what);
 
 /* NCCL communicator of the engines that share one grid, one rank per GPU, slabs in rank order along z (SURVEY §8b "gather()").
  * libnccl.so.2 is loaded at run time, the first time one of these is called (a copy the process already carries - a

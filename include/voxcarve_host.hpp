@@ -160,6 +160,14 @@ class Engine {
     void commInit(int rank, int world, const void* unique_id_128) { check(vc_comm_init(h_, rank, world, unique_id_128)); }
     void exchangeHalos() { check(vc_exchange_halos(h_)); }
     void gather(const std::vector<int32_t>& z_bounds, int what = 1) { check(vc_gather(h_, what, z_bounds.data())); }
+    // engines of this process: everyone pulls the other slabs over NVLink (no NCCL); e.g. before fastCarve-style whole-grid work
+    static void gatherPeer(const std::vector<Engine*>& engines, int what = 1) {
+        std::vector<vc_engine*> hs;
+        for (Engine* e : engines) hs.push_back(e->handle());
+        if (hs.empty()) return;
+        const int rc = vc_gather_peer(hs.data(), (int32_t)hs.size(), what);
+        if (rc != VC_OK) throw Error(rc, vc_last_error(hs[0]));
+    }
     void allreduce(uint64_t* values, int n) { check(vc_comm_allreduce_u64(h_, values, n)); }
     std::vector<uint32_t> downloadFull(int which) {
         std::vector<uint32_t> w((size_t)Z_ * Y_ * wordsPerRow());

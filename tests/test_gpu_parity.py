@@ -972,3 +972,36 @@ def test_masks_from_page_locked_memory_without_a_sync(A, oracle):
             e.carve()          # enqueued right behind the uploads
             assert np.array_equal(e.download_occupied(), ro) and np.array_equal(e.download_seen(), rs), kind
             assert np.array_equal(e.download_masks(), w.mask_bits), kind
+
+
+def test_peer_gather_assembles_the_grid_in_every_engine(A, oracle):
+    """vc_gather_peer: engines of one process (here: three slabs on one device) pull each other's slabs into their whole-grid
+    buffers; every engine then holds the single-engine volumes and runs its consumers on the gathered grid"""
+    from ar_voxel_project_b200.engine import gather_peer
+    from ar_voxel_project_b200.synth import Workload
+    X, Y, Z = 70, 44, 40
+    w = Workload(70, 6, 240, 180, seed=5, dims=(X, Y, Z))
+    occ, seen, hist, nt, _ = _whole_grid_reference(A, w, X, Y, Z, with_images=False)
+    bounds = [0, 9, 26, 40]
+    engines = []
+    try:
+        for z0, z1 in zip(bounds[:-1], bounds[1:]):
+            e = A.VoxelEngine(X, Y, Z, w.s, z_begin=z0, z_end=z1)
+            e.alloc_full_volumes()
+            e.set_views(w.P, w.W, w.H, w.M), e.set_masks_bits(w.mask_bits)
+            e.carve()
+            engines.append(e)
+        with pytest.raises(A.VoxCarveError):
+            engines[1].download_full(0)       # not gathered yet
+        gather_peer(engines[::-1], occupied=True, seen=True)
+        tot = np.zeros(256, np.uint64)
+        for e in engines:
+            assert np.array_equal(e.download_full(0), occ) and np.array_equal(e.download_full(1), seen)
+            e.mc_classify()
+            tot += e.download_mc()[0]
+        assert np.array_equal(tot, hist)
+        with pytest.raises(A.VoxCarveError):
+            gather_peer(engines[:2])          # the slabs must tile the grid
+    finally:
+        for e in engines:
+            e.close()
