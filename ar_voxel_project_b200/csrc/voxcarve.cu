@@ -791,11 +791,10 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
         fp.per_plane = (unsigned)(((long long)e->g.Y * Q + 255) / 256);
     }
     if (fresh && quads) {
-        // one fill block per SM (blocks are dealt round-robin), more when a block would otherwise walk more than ~64 brick layers
-        const unsigned long long units = (unsigned long long)fp.per_plane * (unsigned)nbz;
-        unsigned per_sm = (unsigned)((units + 64ull * e->sm_count - 1) / (64ull * e->sm_count));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > (unsigned)resident / 2) per_sm = resident >= 2 ? (unsigned)resident / 2 : 1;
+        // ONE fill block per SM (blocks are dealt round-robin).  More of them when the slab has many brick layers was the r1
+        // heuristic; measured on C5 (256 layers): 1 / 2 / 3 / 4 fill blocks per SM = 1.90 / 1.96 / 1.99 / 2.02 ms - the kernel is
+        // bound by its computing blocks, so the fill gets as few as keep the stores flowing.
+        const unsigned per_sm = 1;
         fp.n_fill_blocks = (unsigned)e->sm_count * per_sm < pgrid ? (unsigned)e->sm_count * per_sm : pgrid;
     } else if (quads) {
         vc_fill4_kernel<<<dim3(fp.per_plane, (unsigned)nbz), 256, 0, e->stream>>>(fp);  // one block per (256 quads, brick layer)
