@@ -42,15 +42,21 @@ def all_gather_slabs(full, Z, world=None, group=None, bounds=None):
     return full
 
 
-def init_engine_comm(engine, group=None):
-    """Give `engine` its NCCL communicator inside libvoxcarve.so (vc_comm_init): rank 0 makes the id, torch.distributed (any
-    backend) only carries its 128 bytes to the other ranks.  From then on the data path - vc_exchange_halos, vc_gather,
-    vc_comm_allreduce_u64 - runs in the library on the engine's stream; torch is out of it."""
+def broadcast_comm_id(group=None):
+    """rank 0 makes the 128-byte NCCL id (vc_comm_unique_id), every rank of `group` returns the same bytes; any backend"""
     from .engine import comm_unique_id
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rank = dist.get_rank(group)
     box = [comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    engine.comm_init(rank, world, box[0])
+    return box[0]
+
+
+def init_engine_comm(engine, group=None):
+    """Give `engine` its NCCL communicator inside libvoxcarve.so (vc_comm_init): torch.distributed (any backend) only carries
+    the 128 bytes of the id to the other ranks.  From then on the data path - vc_exchange_halos, vc_gather,
+    vc_comm_allreduce_u64 - runs in the library on the engine's stream; torch is out of it."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    engine.comm_init(rank, world, broadcast_comm_id(group))
     return rank, world
 
 

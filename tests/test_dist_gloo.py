@@ -72,6 +72,32 @@ def test_slab_gather_and_histogram_reduce(world, Z):
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
+def _id_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ar_voxel_project_b200.dist import broadcast_comm_id
+        q.put((rank, broadcast_comm_id().hex()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_id_reaches_every_rank():
+    """the plumbing of init_engine_comm without a GPU: rank 0 makes the 128-byte NCCL id inside libvoxcarve.so (NCCL is loaded with
+    dlopen, no device needed for that), gloo carries it, every rank holds the same bytes"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_id_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(res[0]) == 256 and res[0] == res[1] and set(res[0]) != {"0"}
+
+
 def test_slab_ranges_tile_the_grid():
     from ar_voxel_project_b200.dist import slab_range
     for Z in (1, 7, 100, 1024, 2048):
