@@ -505,7 +505,7 @@ int vc_set_masks(vc_engine* e, const void* masks, int32_t format) {
             const long long warps = n_rows * e->Ww;
             vc_pack_bgr_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(d_tmp + (size_t)v0 * view_bgr, m, e->W, e->Ww, n_rows);
         }
-        vc_sat_rowprefix_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(m, t, e->Ww, n_rows);
+        vc_sat_rowprefix_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, e->stream>>>(m, t, e->Ww, n_rows);  // a warp per row
         vc_sat_build_kernel<<<(unsigned)n_cols, 32 * VC_SAT_WARPS, 0, e->stream>>>(m, t, e->d_sat + (size_t)v0 * (e->H + 1) * vc_sat_pitch(e->W), e->W, e->H, e->Ww, nv);
         return cudaGetLastError();
     };
