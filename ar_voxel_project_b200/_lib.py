@@ -25,7 +25,7 @@ class Stats(C.Structure):
                 ("executed_voxel_views", C.c_uint64), ("brick_corner_views", C.c_uint64),
                 ("bricks_total", C.c_uint64), ("bricks_listed", C.c_uint64), ("flood_rounds", C.c_uint64), ("carve_launches", C.c_uint64),
                 ("l2_persist_bytes", C.c_uint64), ("filter_rows", C.c_uint64), ("filter_slow_rows", C.c_uint64),
-                ("filter_mismatches", C.c_uint64), ("subbrick_corner_views", C.c_uint64)]
+                ("filter_mismatches", C.c_uint64), ("subbrick_corner_views", C.c_uint64), ("volumes_compressible", C.c_uint64)]
 
 
 # name -> (restype, argtypes); the single source of truth the symbol-export test checks against the header

@@ -3,6 +3,7 @@
 // There is no CPU path in this library: every entry point needs a CUDA device.
 #include "../../include/voxcarve.h"
 
+#include <cuda.h>             // types only: the few driver entry points used (vol_alloc) are fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>             // types and prototypes only: the library is dlopen-ed by vc_comm_init (see load_nccl)
@@ -13,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -59,6 +61,8 @@ struct vc_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished z-chunks while the next chunk is carving (vc_carve_download)
+    cudaStream_t fill_stream = nullptr;   // vc_blind_fill_kernel of a fresh carve, next to the brick classification
+    cudaEvent_t ev_fill_fork = nullptr, ev_fill_join = nullptr;
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_mid = false;
     // volumes
@@ -176,6 +180,120 @@ bool host_pinned(const void* p) {  // page-locked (cudaHostAlloc / cudaHostRegis
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Volume memory.  The occupancy / seen volumes are written once per carve, almost entirely with uniform words (all occupied,
+// all carved, all seen), and read again by every consumer.  They live in COMPRESSIBLE device memory when the GPU grants it
+// (cuMemCreate + CU_MEM_ALLOCATION_COMP_GENERIC: the L2 compresses uniform lines on their way to HBM), plain cudaMalloc memory
+// otherwise or with VOXCARVE_COMPRESSIBLE=0.  The driver entry points come from cudaGetDriverEntryPoint: no link against libcuda.
+// ---------------------------------------------------------------------------------------------
+struct VmmApi {
+    bool tried = false, ok = false;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MemGetAllocationPropertiesFromHandle)(CUmemAllocationProp*, CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+};
+struct VmmBlock { size_t size; CUmemGenericAllocationHandle handle; };
+static VmmApi g_vmm;
+static std::mutex g_vmm_mutex;
+static std::map<void*, VmmBlock> g_vmm_blocks;
+
+static bool vmm_load() {  // g_vmm_mutex held
+    if (g_vmm.tried) return g_vmm.ok;
+    g_vmm.tried = true;
+    const char* env = getenv("VOXCARVE_COMPRESSIBLE");
+    if (env && env[0] == '0') return false;
+    bool ok = true;
+    auto get = [&](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) { cudaGetLastError(); ok = false; }
+    };
+    get("cuMemCreate", (void**)&g_vmm.MemCreate);
+    get("cuMemRelease", (void**)&g_vmm.MemRelease);
+    get("cuMemAddressReserve", (void**)&g_vmm.MemAddressReserve);
+    get("cuMemAddressFree", (void**)&g_vmm.MemAddressFree);
+    get("cuMemMap", (void**)&g_vmm.MemMap);
+    get("cuMemUnmap", (void**)&g_vmm.MemUnmap);
+    get("cuMemSetAccess", (void**)&g_vmm.MemSetAccess);
+    get("cuMemGetAllocationGranularity", (void**)&g_vmm.MemGetAllocationGranularity);
+    get("cuMemGetAllocationPropertiesFromHandle", (void**)&g_vmm.MemGetAllocationPropertiesFromHandle);
+    get("cuDeviceGetAttribute", (void**)&g_vmm.DeviceGetAttribute);
+    g_vmm.ok = ok;
+    return ok;
+}
+
+// compressible memory on `device` (the current one), readable / writable from every device that can reach it; nullptr = not granted
+static void* vmm_alloc_compressible(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_vmm_mutex);
+    if (!vmm_load()) return nullptr;
+    int supported = 0;
+    if (g_vmm.DeviceGetAttribute(&supported, CU_DEVICE_ATTRIBUTE_GENERIC_COMPRESSION_SUPPORTED, (CUdevice)device) != CUDA_SUCCESS || !supported) return nullptr;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.allocFlags.compressionType = CU_MEM_ALLOCATION_COMP_GENERIC;
+    size_t gran = 0;
+    if (g_vmm.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return nullptr;
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    if (g_vmm.MemCreate(&h, size, &prop, 0) != CUDA_SUCCESS) return nullptr;
+    CUmemAllocationProp got = {};
+    if (g_vmm.MemGetAllocationPropertiesFromHandle(&got, h) != CUDA_SUCCESS || got.allocFlags.compressionType != CU_MEM_ALLOCATION_COMP_GENERIC) { g_vmm.MemRelease(h); return nullptr; }
+    CUdeviceptr va = 0;
+    if (g_vmm.MemAddressReserve(&va, size, 0, 0, 0) != CUDA_SUCCESS) { g_vmm.MemRelease(h); return nullptr; }
+    if (g_vmm.MemMap(va, size, 0, h, 0) != CUDA_SUCCESS) { g_vmm.MemAddressFree(va, size); g_vmm.MemRelease(h); return nullptr; }
+    std::vector<CUmemAccessDesc> acc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess) { cudaGetLastError(); n_dev = device + 1; }
+    for (int d = 0; d < n_dev; d++) {  // the halo / gather copies between engines of one process read and write peers' volumes
+        int can = d == device;
+        if (!can && cudaDeviceCanAccessPeer(&can, d, device) != cudaSuccess) { cudaGetLastError(); can = 0; }
+        if (!can) continue;
+        CUmemAccessDesc a = {};
+        a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        a.location.id = d;
+        a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        acc.push_back(a);
+    }
+    if (g_vmm.MemSetAccess(va, size, acc.data(), acc.size()) != CUDA_SUCCESS) {
+        CUmemAccessDesc a = {};  // at least the owner
+        a.location.type = CU_MEM_LOCATION_TYPE_DEVICE; a.location.id = device; a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (g_vmm.MemSetAccess(va, size, &a, 1) != CUDA_SUCCESS) { g_vmm.MemUnmap(va, size); g_vmm.MemAddressFree(va, size); g_vmm.MemRelease(h); return nullptr; }
+    }
+    g_vmm_blocks[(void*)va] = VmmBlock{size, h};
+    return (void*)va;
+}
+
+static cudaError_t vol_alloc(vc_engine* e, uint32_t** out, size_t bytes) {
+    *out = (uint32_t*)vmm_alloc_compressible(e->g.device, bytes);
+    if (*out) { e->stats.volumes_compressible = 1; return cudaSuccess; }
+    e->stats.volumes_compressible = 0;
+    return cudaMalloc(out, bytes);
+}
+static void vol_free(uint32_t* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_vmm_mutex);
+        auto it = g_vmm_blocks.find((void*)p);
+        if (it != g_vmm_blocks.end()) {
+            cudaDeviceSynchronize();  // cudaFree's implicit wait for work in flight, restated
+            g_vmm.MemUnmap((CUdeviceptr)p, it->second.size);
+            g_vmm.MemAddressFree((CUdeviceptr)p, it->second.size);
+            g_vmm.MemRelease(it->second.handle);
+            g_vmm_blocks.erase(it);
+            return;
+        }
+    }
+    cudaFree(p);
 }
 
 // upload this engine's view constants if another engine (or an older version) owns them
@@ -387,13 +505,13 @@ void vc_destroy(vc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->g.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
+    vol_free(e->d_occ_own); vol_free(e->d_seen_own); cudaFree(e->d_mask); cudaFree(e->d_images);
     cudaFree(e->d_sat); cudaFree(e->d_sat_tmp); cudaFree(e->d_bgr_tmp); cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     cudaFree(e->d_block_sums);
     cudaFree(e->d_scalars); cudaFree(e->d_hist); cudaFree(e->d_filt); cudaFree(e->d_view64);
     cudaFree(e->d_dense); cudaFree(e->d_dense_tmp); cudaFree(e->d_mesh_verts); cudaFree(e->d_mesh_rgb);
     cudaFree(e->d_sparse_idx); cudaFree(e->d_sparse_words);
-    cudaFree(e->d_scratch); cudaFree(e->d_undist_ir); cudaFree(e->d_occ_full_own); cudaFree(e->d_seen_full_own); cudaFree(e->d_reduce);
+    cudaFree(e->d_scratch); cudaFree(e->d_undist_ir); vol_free(e->d_occ_full_own); vol_free(e->d_seen_full_own); cudaFree(e->d_reduce);
     if (e->comm) vc_comm_destroy(e);
     for (CarveGraphSlot& gs : e->graph_slot) if (gs.exec) cudaGraphExecDestroy(gs.exec);
     if (e->ev_halo) cudaEventDestroy(e->ev_halo);
@@ -403,6 +521,9 @@ void vc_destroy(vc_engine* e) {
     if (e->evm) cudaEventDestroy(e->evm);
     for (int c = 0; c < 4; c++) if (e->ev_chunk[c]) cudaEventDestroy(e->ev_chunk[c]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_fill_fork) cudaEventDestroy(e->ev_fill_fork);
+    if (e->ev_fill_join) cudaEventDestroy(e->ev_fill_join);
+    if (e->fill_stream) cudaStreamDestroy(e->fill_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     {
         std::lock_guard<std::mutex> lk(g_const_mutex);
@@ -610,8 +731,8 @@ static cudaError_t undistort_device(const uint8_t* d_src, uint8_t* d_dst, int n,
 static int ensure_volumes(vc_engine* e) {
     if (e->d_occ_full || e->d_occ_own) return VC_OK;
     if (bind_device(e)) return VC_ERR_CUDA;
-    VC_CUDA(e, cudaMalloc(&e->d_occ_own, (e->slab_words + 2 * e->plane_words) * 4));  // + the halo planes z_begin - 1 and z_end
-    VC_CUDA(e, cudaMalloc(&e->d_seen_own, e->slab_words * 4));
+    VC_CUDA(e, vol_alloc(e, &e->d_occ_own, (e->slab_words + 2 * e->plane_words) * 4));  // + the halo planes z_begin - 1 and z_end
+    VC_CUDA(e, vol_alloc(e, &e->d_seen_own, e->slab_words * 4));
     return VC_OK;
 }
 
@@ -716,6 +837,11 @@ static int ensure_brick_buffers(vc_engine* e) {
     if (e->resident_blocks < 1) {  // persistent grid of vc_carve_bricks: as many blocks of 8 warps as are resident at once
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resident_blocks, vc_carve_bricks<false>, 256, 0) != cudaSuccess || e->resident_blocks < 1) { cudaGetLastError(); e->resident_blocks = 2; }
     }
+    if (!e->fill_stream) {
+        VC_CUDA(e, cudaStreamCreateWithFlags(&e->fill_stream, cudaStreamNonBlocking));
+        VC_CUDA(e, cudaEventCreateWithFlags(&e->ev_fill_fork, cudaEventDisableTiming));
+        VC_CUDA(e, cudaEventCreateWithFlags(&e->ev_fill_join, cudaEventDisableTiming));
+    }
     if (e->d_bricks) return VC_OK;
     VC_CUDA(e, cudaMalloc(&e->d_bricks, (size_t)n_bricks * sizeof(VcBrickState)));
     VC_CUDA(e, cudaMalloc(&e->d_super, (size_t)n_super * sizeof(VcBrickState)));
@@ -741,6 +867,11 @@ static VcCarveParams carve_params(vc_engine* e, int view_begin, int view_end) {
     return p;
 }
 
+static bool blind_fill_enabled() {  // VOXCARVE_BLIND_FILL=0: the r1 scheme (flag-driven fill by the first blocks of vc_carve_bricks), for comparison
+    static const bool off = [] { const char* v = getenv("VOXCARVE_BLIND_FILL"); return v && v[0] == '0'; }();
+    return !off;
+}
+
 // VC_EXACT on the planes [zl0, zl1) of the slab (zl0 a multiple of the super-brick height, so bricks sit where they
 // would in a whole-slab pass): classify super-bricks, classify bricks, fill, evaluate the undecided pairs.
 static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bool count, bool fresh, bool record_mid, uint64_t* n_bricks_out) {
@@ -754,6 +885,24 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     if (p.nz > 65535) return fail(e, VC_ERR_ARG, "vc_carve: slab of %d planes exceeds the fill grid", p.nz);
     unsigned int* d_nlist = (unsigned int*)(e->d_scalars + 6);   // [6] = front list length | super-list length, [7] = work counter | back list length
     unsigned int* d_work = (unsigned int*)(e->d_scalars + 7);
+    // Fresh carve: most words end up "carved and seen".  That pattern is written everywhere first, by a kernel that needs nothing
+    // from the classification and runs next to it on a second stream (a fork / join the graph capture follows); the fill pass
+    // inside vc_carve_bricks then only writes the words of bricks that are neither carved nor listed.
+    const bool blind = fresh && e->Wx % 4 == 0 && blind_fill_enabled();
+    if (blind) {
+        const unsigned Q = (unsigned)e->Wx / 4u;
+        int q_shift = -1;
+        for (int b = 0; b < 31; b++) if (Q == (1u << b)) q_shift = b;
+        const int rem = e->g.X - (e->Wx - 1) * 32;
+        const size_t n_quads = (size_t)p.nz * e->g.Y * Q;
+        VC_CUDA(e, cudaEventRecord(e->ev_fill_fork, e->stream));
+        VC_CUDA(e, cudaStreamWaitEvent(e->fill_stream, e->ev_fill_fork, 0));
+        const unsigned bgrid = (unsigned)std::min<size_t>((n_quads + 255) / 256, (size_t)e->sm_count);  // one block per SM reaches the memory's write rate and leaves room for the classification's blocks
+        vc_blind_fill_kernel<<<bgrid, 256, 0, e->fill_stream>>>((uint4*)p.occ, (uint4*)p.seen, n_quads, Q, q_shift, rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u));
+        VC_CUDA(e, cudaGetLastError());
+        VC_CUDA(e, cudaEventRecord(e->ev_fill_join, e->fill_stream));
+        e->stats.carve_launches += 1;
+    }
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
     VcBrickParams bp{};
     bp.list = e->d_bricks; bp.n_list = d_nlist; bp.n_list_back = d_work + 1; bp.list_cap = (unsigned)n_bricks;
@@ -784,6 +933,8 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     fp.occ = p.occ; fp.seen = p.seen; fp.brick_flags = e->d_brick_flags; fp.super_flags = e->d_super_flags;
     fp.X = e->g.X; fp.Y = e->g.Y; fp.Wx = e->Wx; fp.nby = nby; fp.pbx = sbx; fp.pby = sby;
     fp.fresh = fresh ? 1 : 0; fp.skip_listed = fresh ? 1 : 0; fp.nz = p.nz; fp.q_shift = -1; fp.n_fill_blocks = 0;
+    fp.blind = blind ? 1 : 0;
+    if (blind) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_fill_join, 0));  // before anything else writes the volumes
     const bool quads = e->Wx % 4 == 0;
     if (quads) {
         const unsigned Q = (unsigned)e->Wx / 4u;
@@ -900,7 +1051,7 @@ int vc_carve(vc_engine* e, int32_t mode, int32_t view_begin, int32_t view_end, i
                 gs.valid = true;
             }
             VC_CUDA(e, cudaGraphLaunch(gs.exec, e->stream));
-            if (!captured_now) e->stats.carve_launches += (fresh && e->Wx % 4 == 0) ? 3 : 4;  // the capture counted its own
+            if (!captured_now) e->stats.carve_launches += (fresh && e->Wx % 4 == 0 && !blind_fill_enabled()) ? 3 : 4;  // the capture counted its own
             const int nby = (e->g.Y + VC_BY - 1) / VC_BY, nbz = (e->nz + VC_BZ - 1) / VC_BZ;
             e->stats.bricks_total = (uint64_t)e->Wx * nby * nbz;
             e->have_mid = false;
@@ -1124,7 +1275,7 @@ int vc_set_slab(vc_engine* e, int32_t z_begin, int32_t z_end) {
     e->nz = z_end - z_begin;
     e->slab_words = e->plane_words * e->nz;
     // everything sized by the slab is dropped and re-created on demand; views, masks and SAT stay
-    cudaFree(e->d_occ_own); cudaFree(e->d_seen_own); e->d_occ_own = e->d_seen_own = nullptr;
+    vol_free(e->d_occ_own); vol_free(e->d_seen_own); e->d_occ_own = e->d_seen_own = nullptr;
     cudaFree(e->d_bricks); cudaFree(e->d_super); cudaFree(e->d_brick_flags); cudaFree(e->d_super_flags); cudaFree(e->d_super_list);
     e->d_bricks = nullptr; e->d_super = nullptr; e->d_brick_flags = nullptr; e->d_super_flags = nullptr; e->d_super_list = nullptr;
     cudaFree(e->d_block_sums);
@@ -1197,7 +1348,7 @@ int vc_bind_volumes(vc_engine* e, void* d_occupied_full, void* d_seen_full) {
     if (bind_device(e)) return VC_ERR_CUDA;
     VC_CUDA(e, cudaStreamSynchronize(e->stream));
     if (e->d_occ_full_own && d_occupied_full != e->d_occ_full_own) {  // replaces engine-owned whole-grid buffers
-        cudaFree(e->d_occ_full_own); cudaFree(e->d_seen_full_own);
+        vol_free(e->d_occ_full_own); vol_free(e->d_seen_full_own);
         e->d_occ_full_own = e->d_seen_full_own = nullptr;
     }
     e->d_occ_full = (uint32_t*)d_occupied_full;
@@ -1711,13 +1862,13 @@ int vc_alloc_full_volumes(vc_engine* e) {
     if (e->d_occ_full_own) return VC_OK;
     const size_t bytes = (size_t)e->g.Z * e->plane_words * 4;
     uint32_t *o = nullptr, *s = nullptr;
-    VC_CUDA(e, cudaMalloc(&o, bytes));
-    if (cudaMalloc(&s, bytes) != cudaSuccess) { cudaFree(o); cudaGetLastError(); return fail(e, VC_ERR_CUDA, "vc_alloc_full_volumes: out of device memory (%zu bytes per volume)", bytes); }
+    VC_CUDA(e, vol_alloc(e, &o, bytes));
+    if (vol_alloc(e, &s, bytes) != cudaSuccess) { vol_free(o); cudaGetLastError(); return fail(e, VC_ERR_CUDA, "vc_alloc_full_volumes: out of device memory (%zu bytes per volume)", bytes); }
     int rc = vc_bind_volumes(e, o, s);  // drops the slab-sized volumes' role; resets the state
-    if (rc) { cudaFree(o); cudaFree(s); return rc; }
+    if (rc) { vol_free(o); vol_free(s); return rc; }
     e->d_occ_full_own = o;
     e->d_seen_full_own = s;
-    cudaFree(e->d_occ_own); cudaFree(e->d_seen_own);
+    vol_free(e->d_occ_own); vol_free(e->d_seen_own);
     e->d_occ_own = e->d_seen_own = nullptr;
     return VC_OK;
 }

@@ -91,6 +91,8 @@ typedef struct vc_stats {
     uint64_t filter_slow_rows;
     uint64_t filter_mismatches;
     uint64_t subbrick_corner_views; /* the part of brick_corner_views spent inside vc_carve_bricks (8x8x8 sub-brick level) */
+    uint64_t volumes_compressible;  /* 1: the engine-owned volumes live in compressible device memory (cuMemCreate, generic compression),
+                                       0: plain cudaMalloc memory (not granted by the GPU, or VOXCARVE_COMPRESSIBLE=0 in the environment) */
 } vc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------- */
