@@ -1005,3 +1005,52 @@ def test_peer_gather_assembles_the_grid_in_every_engine(A, oracle):
     finally:
         for e in engines:
             e.close()
+
+
+def test_fill_schemes_and_volume_memory_agree(A, oracle):
+    """The fresh carve's fill (blind 'carved and seen' pass next to the classification + patch, volumes in compressible memory
+    when the GPU grants it) against the flag-driven fill in plain cudaMalloc memory (VOXCARVE_BLIND_FILL=0,
+    VOXCARVE_COMPRESSIBLE=0: read once per process, hence the subprocesses) and against the oracle - whole grid, a ragged
+    slab with a partial last word, a grid whose rows are not whole quads (no blind pass there), twice in a row (graph replay)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = r'''
+import hashlib, json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import ar_voxel_project_b200 as A
+from ar_voxel_project_b200.synth import Workload
+out = {}
+for name, dims, slab in (("cube", (256, 256, 256), None), ("slab7", (200, 130, 150), (37, 120)), ("slabq", (250, 70, 90), (13, 77))):
+    w = Workload(max(dims), 10, 320, 240, seed=5, dims=dims)
+    z0, z1 = slab if slab else (0, dims[2])
+    with A.VoxelEngine(*dims, w.s, z_begin=z0, z_end=z1) as e:
+        e.set_views(w.P, w.W, w.H)
+        e.set_masks_bits(w.mask_bits)
+        hs = []
+        for rep in range(2):
+            e.reset()
+            e.carve(0)
+            hs.append(hashlib.sha256(e.download_occupied().tobytes() + e.download_seen().tobytes()).hexdigest())
+        assert hs[0] == hs[1]
+        out[name] = hs[0]
+        out[name + "_compressible"] = int(e.stats()["volumes_compressible"])
+print(json.dumps(out))
+''' % ROOT
+    res = {}
+    for tag, env in (("default", {}), ("plain", {"VOXCARVE_BLIND_FILL": "0", "VOXCARVE_COMPRESSIBLE": "0"}), ("blind_plain_memory", {"VOXCARVE_COMPRESSIBLE": "0"})):
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600, env={**os.environ, **env})
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    for name in ("cube", "slab7", "slabq"):
+        assert res["default"][name] == res["plain"][name] == res["blind_plain_memory"][name], (name, res)
+    assert res["plain"]["cube_compressible"] == 0
+    # ... and the default against the oracle (the other parity tests all run the default too)
+    import hashlib
+    from ar_voxel_project_b200.synth import Workload
+    dims, (z0, z1) = (250, 70, 90), (13, 77)
+    w = Workload(max(dims), 10, 320, 240, seed=5, dims=dims)
+    ro, rs = oracle.carve(*dims, w.s, w.P, w.W, w.H, mask_bits=w.mask_bits, z0=z0, z1=z1)
+    assert hashlib.sha256(ro.tobytes() + rs.tobytes()).hexdigest() == res["default"]["slabq"]
