@@ -403,9 +403,8 @@ def run_ours(args):
     Wx = (X + 31) // 32
     nominal_total = X * Y * Z * V
 
-    # whole-grid device buffers (torch = plumbing): slabs are carved in place, gathered in place
-    occ_full = torch.empty((Z, Y, Wx), dtype=torch.int32, device=dev)
-    seen_full = torch.empty_like(occ_full)
+    # whole-grid device buffers owned by the engine (vc_alloc_full_volumes: compressible memory when the GPU grants it): slabs are
+    # carved in place, gathered in place
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # every rank holds all views; z-slab boundaries come from the engine's planner (super-brick classification of the
     # whole grid, identical on every rank) so that the per-voxel work, not the plane count, is balanced
@@ -421,7 +420,7 @@ def run_ours(args):
     # single-GPU result of the same job, hashed: what the gathered grid of an N > 1 run must equal (rank 0, before the slabs)
     ref_hash = None
     if rank == 0:
-        eng.bind_volumes(occ_full.data_ptr(), seen_full.data_ptr())
+        eng.alloc_full_volumes()
         eng.reset(), eng.carve(A._lib.VC_EXACT)
         ref_hash = {"occupied": grid_hash(eng.download_occupied()), "seen": grid_hash(eng.download_seen())}
     z0, z1 = bounds[rank], bounds[rank + 1]
@@ -429,7 +428,7 @@ def run_ours(args):
         eng.set_slab(z0, z1)
         from ar_voxel_project_b200.dist import init_engine_comm
         init_engine_comm(eng)   # NCCL communicator inside libvoxcarve.so; torch only carried its 128-byte id
-    eng.bind_volumes(occ_full.data_ptr(), seen_full.data_ptr())
+    eng.alloc_full_volumes()
 
     def step():
         eng.reset()
@@ -456,7 +455,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     clk = clocks.stop()
     clk["sampled_over"] = f"{args.warmup} warm-up + {args.steps} timed + {n_tail} identical untimed steps"
-    launches = 3 * args.steps  # vc_brick_classify_kernel<1>, <0>, vc_carve_bricks (its first blocks do the fill pass, which absorbs the reset), per step
+    launches = 4 * args.steps  # vc_blind_fill_kernel (absorbs the reset), vc_brick_classify_kernel<1>, <0>, vc_carve_bricks (its first blocks patch the words the blind fill got wrong), per step
 
     for _ in range(2):
         step_with_consumer()
@@ -488,6 +487,7 @@ def run_ours(args):
     eng.reset()
     eng.carve(A._lib.VC_EXACT, count_executed=True)
     st = eng.stats()
+    volumes_compressible = int(st["volumes_compressible"])
     executed_total = allsum(float(st["executed_voxel_views"]))
     corner_total = allsum(float(st["brick_corner_views"]))
     sub_corner_total = allsum(float(st["subbrick_corner_views"]))
@@ -568,6 +568,7 @@ def run_ours(args):
     e2e = None
     e2e_bgr = None
     e2e_dense = None
+    noncarved_bricks_total = None
     if not args.no_e2e:
         out_occ = torch.empty((z1 - z0, Y, Wx), dtype=torch.int32).pin_memory()
         out_seen = torch.empty_like(out_occ).pin_memory()
@@ -633,6 +634,7 @@ def run_ours(args):
         if not sparse_ok:
             raise SystemExit("bench.py: the expanded sparse result differs from the dense volumes")
         sparse_d2h = int(flags_p.numel() + sparse_n[0] * (4 + 512))
+        noncarved_bricks_total = allsum(float(((np.asarray(f_) & 1) == 0).sum()))  # bricks whose words vc_carve_bricks writes (patch pass + work items)
         h2d_bits = int(bits_pinned.numel() * 4 + w.P.nbytes + w.M.nbytes)
         h2d_bgr = int(bgr.numel() + w.P.nbytes + w.M.nbytes)
         # kernels per e2e step: [pack_bgr] + 3 SAT passes + 2 classify + carve_bricks + flag resolve + pack  (dense: 4 z-chunks x (2 classify + fill + carve_bricks))
@@ -640,13 +642,13 @@ def run_ours(args):
                "input": "cached bit-packed undistorted silhouettes (VC_MASK_BITS) + P/M, pinned host memory",
                "result": f"sparse: one flag byte per 32x8x8-voxel brick + occupied/seen words of the {sparse_n[0]} listed bricks (vc_carve_download_sparse); "
                          "expands to exactly the dense volumes (checked after the timed region), which include/voxcarve_host.hpp applies to the Model brick by brick",
-               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download_sparse", "gpu_launches": 8 * args.steps,
+               "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download_sparse", "gpu_launches": 9 * args.steps,
                "result_identical_to_dense": sparse_ok, "host_expand_numpy_ms_untimed": expand_ms}
         e2e_bgr = {"value": nominal_total / s_sparse_bgr, "unit": UNIT, "h2d_bytes_per_step": h2d_bgr, "d2h_bytes_per_step": sparse_d2h, "ms_per_step": s_sparse_bgr * 1e3,
-                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "result": "sparse", "gpu_launches": 9 * args.steps}
+                   "input": "8UC3 undistorted masks (VC_MASK_BGR8), packed on device", "result": "sparse", "gpu_launches": 10 * args.steps}
         e2e_dense = {"bits": {"value": nominal_total / s_bits, "ms_per_step": s_bits * 1e3, "h2d_bytes_per_step": h2d_bits, "d2h_bytes_per_step": int(d2h),
-                              "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download (both volumes as plain words, z-chunks overlapped with PCIe)", "gpu_launches": 15 * args.steps},
-                     "bgr8": {"value": nominal_total / s_bgr, "ms_per_step": s_bgr * 1e3, "h2d_bytes_per_step": h2d_bgr, "d2h_bytes_per_step": int(d2h), "gpu_launches": 16 * args.steps}}
+                              "call": "vc_set_views + vc_set_masks + vc_reset + vc_carve_download (both volumes as plain words, z-chunks overlapped with PCIe)", "gpu_launches": 19 * args.steps},
+                     "bgr8": {"value": nominal_total / s_bgr, "ms_per_step": s_bgr * 1e3, "h2d_bytes_per_step": h2d_bgr, "d2h_bytes_per_step": int(d2h), "gpu_launches": 20 * args.steps}}
         if noisy:   # the hostile masks only exist as 8UC3: that path is the headline e2e of this config
             e2e, e2e_bgr = e2e_bgr, e2e
         eng.set_masks_bits(w.mask_bits)
@@ -676,9 +678,14 @@ def run_ours(args):
         ach = exec_rank * F_ALG / fine_s / 1e12
         vol_bytes = 2.0 * (Z / world) * Y * Wx * 4
         alg_bytes = vol_bytes + w.mask_bits.nbytes
-        # what vc_carve_bricks itself has to move: it writes every word of both volumes (its first blocks run the fill pass),
-        # reads each silhouette bit it tests at least once (<= the mask set) and four summed-area-table corners per sub-brick test
+        # what vc_carve_bricks itself has to move: vc_blind_fill_kernel has written "carved and seen" everywhere, so the kernel writes
+        # the words of the bricks that are not carved as a whole (patch pass of its first blocks + the work items' listed bricks: 64
+        # words per brick and volume), reads each silhouette bit it tests at least once (<= the mask set) and four summed-area-table
+        # corners per sub-brick test
         sat_bytes = sub_corner_total / world / 8.0 * 16.0
+        if noncarved_bricks_total is None:  # --no-e2e: no flag bytes at hand; every occupied voxel lies in such a brick (2048 voxels each)
+            noncarved_bricks_total = max(bricks_listed, occupied_total / 2048.0)
+        brick_bytes = noncarved_bricks_total / world * 64 * 4 * 2
         cfg = config_dict(w, world, args.config)
         cfg["workload"] = workload_name(w)
         out = {
@@ -694,24 +701,27 @@ def run_ours(args):
             "executed_voxel_views": executed_total, "executed_fraction": executed_total / nominal_total,
             "executed_value": executed_total / (ms_per_step * 1e-3),
             "occupied_voxels": occupied_total, "carve_kernel_ms": kernel_ms_max, "grid_hash": hashes,
-            "kernels_ms": {"vc_brick_classify_kernel<1>+<0>": classify_ms_max, "vc_carve_bricks (incl. the fill pass)": fine_ms_max,
+            "kernels_ms": {"vc_brick_classify_kernel<1>+<0> (vc_blind_fill_kernel runs beside them on a second stream)": classify_ms_max,
+                           "vc_carve_bricks (incl. its patch pass and the wait for the rest of the blind fill)": fine_ms_max,
                            "flat_vc_carve_rows_same_job": flat_ms},
             "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total,
                        "of_which_sub_brick_level": sub_corner_total},
             "filter": {"evaluations_x32": filter_rows, "exact_reevaluations_x32": filter_slow, "mismatches_vs_exact": filter_bad,
                        "note": "per-voxel f32 filter with rigorous radius; every decision cross-checked against the exact path in the counting run"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma if ffma else None,
-                         "traffic": traffic, "algorithmic_bytes": vol_bytes + w.mask_bits.nbytes + sat_bytes,
-                         "algorithmic_bytes_parts": {"volumes_written_once": vol_bytes, "silhouette_bits_read_once": w.mask_bits.nbytes, "sat_corners_of_sub_brick_tests": sat_bytes},
+                         "traffic": traffic, "algorithmic_bytes": brick_bytes + w.mask_bits.nbytes + sat_bytes,
+                         "algorithmic_bytes_parts": {"words_of_bricks_not_carved_as_a_whole": brick_bytes, "silhouette_bits_read_once": w.mask_bits.nbytes, "sat_corners_of_sub_brick_tests": sat_bytes},
+                         "blind_fill": {"kernel": "vc_blind_fill_kernel", "bytes": vol_bytes, "note": "both volumes written once with the 'carved and seen' pattern next to the classification; in compressible memory its DRAM traffic is a fraction of that (profiles/traffic.json)", "volumes_compressible": volumes_compressible},
                          "kernel": "vc_carve_bricks",
                          "peak_source": "FFMA microbenchmark on this GPU (vc_measure_peaks); MEASURED_PEAKS.json carries no FP32 CUDA-core entry",
                          "how": f"projections of one vc_carve_bricks launch ({exec_rank:.4g}: per-voxel + sub-brick corners) x {F_ALG:.0f} FLOP / its time "
-                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve; the kernel's first blocks also do the fill pass); peak = FFMA microbenchmark on this GPU "
+                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve: from the end of the classification to the end of the carve, i.e. incl. the kernel's patch pass and its wait for the blind fill); peak = FFMA microbenchmark on this GPU "
                                 f"(vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s. The kernel is issue-bound, see profiles/"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": vol_bytes / 3.68e12 * 1e3,
+                             "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": vol_bytes / 6.4e12 * 1e3,
                              "how": f"grid-write bound: occupied+seen slab written once + masks read once = {alg_bytes / 1e6:.1f} MB / kernel time; peak = {hbm_src}; "
-                                    "write_only_floor_ms = the two volumes at the 3.68 TB/s a cudaMemset reaches on this GPU (tools/memset_bench.py)"},
+                                    "write_only_floor_ms = the two volumes at the 6.4 TB/s a store-only kernel reaches on this GPU (tools/experiments/fill_pattern_probe.cu, "
+                                    "profiles/r2B_fill_probes.txt); vc_blind_fill_kernel runs at that rate"},
             "gather": gather, "mc_classify_ms": mc_ms, "mc_triangles": mc_tris, "color_ms": color_ms, "per_rank": per_rank,
             "e2e": e2e, "e2e_bgr8": e2e_bgr, "e2e_dense": e2e_dense, "gpu_launches": launches, "clocks": clk,
         }
