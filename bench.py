@@ -478,6 +478,10 @@ def run_ours(args):
     eng.set_profiling(True)   # plain launches with an event between classification and per-voxel kernel (the timed steps above ran the cached CUDA graph)
     for _ in range(5):
         flush.fill_(1)
+        # launched onto an idle GPU: plain launches queued up behind a running kernel start the blind fill and the classification at
+        # the same instant and then run up to 1.6x slower than the graph does (tools/experiments/profile_split_probe.py);
+        # the split below is a diagnostic of the graph's step, so it must add up to it
+        torch.cuda.synchronize()
         step()
         st = eng.stats()
         kt.append(st["last_carve_ms"]), ct.append(st["last_classify_ms"])
