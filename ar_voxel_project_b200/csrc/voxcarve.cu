@@ -889,18 +889,29 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     // from the classification and runs next to it on a second stream (a fork / join the graph capture follows); the fill pass
     // inside vc_carve_bricks then only writes the words of bricks that are neither carved nor listed.
     const bool blind = fresh && e->Wx % 4 == 0 && blind_fill_enabled();
+    bool fill_forked = false;
     if (blind) {
         const unsigned Q = (unsigned)e->Wx / 4u;
         int q_shift = -1;
         for (int b = 0; b < 31; b++) if (Q == (1u << b)) q_shift = b;
         const int rem = e->g.X - (e->Wx - 1) * 32;
         const size_t n_quads = (size_t)p.nz * e->g.Y * Q;
-        VC_CUDA(e, cudaEventRecord(e->ev_fill_fork, e->stream));
-        VC_CUDA(e, cudaStreamWaitEvent(e->fill_stream, e->ev_fill_fork, 0));
+        // As a branch of the captured graph it runs next to the classification.  Plain launches (profiling mode, VOXCARVE_NO_GRAPH,
+        // the z-chunks of vc_carve_download) keep it in stream order instead: queued up behind a running kernel, the two-stream
+        // version of the same sequence measured up to 1.6x slower than the graph (tools/experiments/profile_split_probe.py), and
+        // the two do not overlap anyway (both wait for the memory).
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        VC_CUDA(e, cudaStreamIsCapturing(e->stream, &cap));
+        fill_forked = cap == cudaStreamCaptureStatusActive;
+        cudaStream_t fs = fill_forked ? e->fill_stream : e->stream;
+        if (fill_forked) {
+            VC_CUDA(e, cudaEventRecord(e->ev_fill_fork, e->stream));
+            VC_CUDA(e, cudaStreamWaitEvent(e->fill_stream, e->ev_fill_fork, 0));
+        }
         const unsigned bgrid = (unsigned)std::min<size_t>((n_quads + 255) / 256, (size_t)e->sm_count);  // one block per SM reaches the memory's write rate and leaves room for the classification's blocks
-        vc_blind_fill_kernel<<<bgrid, 256, 0, e->fill_stream>>>((uint4*)p.occ, (uint4*)p.seen, n_quads, Q, q_shift, rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u));
+        vc_blind_fill_kernel<<<bgrid, 256, 0, fs>>>((uint4*)p.occ, (uint4*)p.seen, n_quads, Q, q_shift, rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u));
         VC_CUDA(e, cudaGetLastError());
-        VC_CUDA(e, cudaEventRecord(e->ev_fill_join, e->fill_stream));
+        if (fill_forked) VC_CUDA(e, cudaEventRecord(e->ev_fill_join, e->fill_stream));
         e->stats.carve_launches += 1;
     }
     VC_CUDA(e, cudaMemsetAsync(e->d_scalars + 6, 0, 2 * sizeof(unsigned long long), e->stream));
@@ -934,7 +945,7 @@ static int carve_exact_range(vc_engine* e, VcCarveParams p, int zl0, int zl1, bo
     fp.X = e->g.X; fp.Y = e->g.Y; fp.Wx = e->Wx; fp.nby = nby; fp.pbx = sbx; fp.pby = sby;
     fp.fresh = fresh ? 1 : 0; fp.skip_listed = fresh ? 1 : 0; fp.nz = p.nz; fp.q_shift = -1; fp.n_fill_blocks = 0;
     fp.blind = blind ? 1 : 0;
-    if (blind) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_fill_join, 0));  // before anything else writes the volumes
+    if (fill_forked) VC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_fill_join, 0));  // before anything else writes the volumes
     const bool quads = e->Wx % 4 == 0;
     if (quads) {
         const unsigned Q = (unsigned)e->Wx / 4u;

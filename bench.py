@@ -478,10 +478,7 @@ def run_ours(args):
     eng.set_profiling(True)   # plain launches with an event between classification and per-voxel kernel (the timed steps above ran the cached CUDA graph)
     for _ in range(5):
         flush.fill_(1)
-        # launched onto an idle GPU: plain launches queued up behind a running kernel start the blind fill and the classification at
-        # the same instant and then run up to 1.6x slower than the graph does (tools/experiments/profile_split_probe.py);
-        # the split below is a diagnostic of the graph's step, so it must add up to it
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()  # plain launches onto an idle GPU; the blind fill runs in front of the classification here
         step()
         st = eng.stats()
         kt.append(st["last_carve_ms"]), ct.append(st["last_classify_ms"])
@@ -705,8 +702,8 @@ def run_ours(args):
             "executed_voxel_views": executed_total, "executed_fraction": executed_total / nominal_total,
             "executed_value": executed_total / (ms_per_step * 1e-3),
             "occupied_voxels": occupied_total, "carve_kernel_ms": kernel_ms_max, "grid_hash": hashes,
-            "kernels_ms": {"vc_brick_classify_kernel<1>+<0> (vc_blind_fill_kernel runs beside them on a second stream)": classify_ms_max,
-                           "vc_carve_bricks (incl. its patch pass and the wait for the rest of the blind fill)": fine_ms_max,
+            "kernels_ms": {"vc_blind_fill_kernel + vc_brick_classify_kernel<1> + <0> (plain launches, in stream order; the graph of the timed steps runs the fill beside the other two)": classify_ms_max,
+                           "vc_carve_bricks (incl. its patch pass)": fine_ms_max,
                            "flat_vc_carve_rows_same_job": flat_ms},
             "bricks": {"total": bricks_total, "needing_per_voxel_work": bricks_listed, "corner_projections": corner_total,
                        "of_which_sub_brick_level": sub_corner_total},
@@ -719,7 +716,7 @@ def run_ours(args):
                          "kernel": "vc_carve_bricks",
                          "peak_source": "FFMA microbenchmark on this GPU (vc_measure_peaks); MEASURED_PEAKS.json carries no FP32 CUDA-core entry",
                          "how": f"projections of one vc_carve_bricks launch ({exec_rank:.4g}: per-voxel + sub-brick corners) x {F_ALG:.0f} FLOP / its time "
-                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve: from the end of the classification to the end of the carve, i.e. incl. the kernel's patch pass and its wait for the blind fill); peak = FFMA microbenchmark on this GPU "
+                                f"({fine_ms_max:.3f} ms, CUDA events inside vc_carve: from the end of the classification to the end of the carve, i.e. the kernel with its patch pass); peak = FFMA microbenchmark on this GPU "
                                 f"(vc_measure_peaks); DFMA peak {dfma:.1f} TFLOP/s. The kernel is issue-bound, see profiles/"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / kt_s / 1e9 / hbm_peak, "traffic": None, "write_only_floor_ms": vol_bytes / 6.4e12 * 1e3,
