@@ -105,9 +105,13 @@ VC_EXPORT int vc_api_version(void);
 VC_EXPORT int vc_set_stream(vc_engine* e, void* cuda_stream);
 VC_EXPORT int vc_synchronize(vc_engine* e);
 /* Profiling mode (off by default).  Off: a whole-range VC_EXACT carve is launched as ONE cached CUDA graph (counter reset + the
- * two classification kernels + the per-voxel kernel; re-captured whenever grid, slab, views, buffers or stream arguments
- * change; VOXCARVE_NO_GRAPH=1 in the environment disables it) and vc_stats.last_classify_ms stays 0.  On: plain launches with
- * an event between classification and per-voxel kernel, so that vc_stats splits the carve time and ncu sees every launch. */
+ * blind fill of a fresh carve on a branch of its own + the two classification kernels + the per-voxel kernel; re-captured
+ * whenever grid, slab, views, buffers or stream arguments change; VOXCARVE_NO_GRAPH=1 in the environment disables it) and
+ * vc_stats.last_classify_ms stays 0.  On: plain launches in stream order with an event between classification and per-voxel
+ * kernel, so that vc_stats splits the carve time and ncu sees every launch.
+ * Other environment switches, read once per process, for comparisons: VOXCARVE_BLIND_FILL=0 (fresh carve: the words of all
+ * non-listed bricks written by the first blocks of the per-voxel kernel from the flags, instead of the 'carved and seen' pattern
+ * everywhere first + a patch pass), VOXCARVE_COMPRESSIBLE=0 (engine-owned volumes in plain cudaMalloc memory). */
 VC_EXPORT int vc_set_profiling(vc_engine* e, int32_t on);
 
 /* ---- inputs ---------------------------------------------------------------------- */
@@ -121,7 +125,7 @@ VC_EXPORT int vc_set_views(vc_engine* e, int32_t V, int32_t W, int32_t H, const 
  * bit x&31 of word x>>5, 1 = background (pixel == (0,0,0), VoxelCarving.cpp:50).
  * VC_MASK_BGR8: the 8UC3 images themselves, uint8[V][H][W][3]; packed on the device. HOST memory (VC_MASK_BITS also takes a
  * DEVICE pointer: silhouettes that a segmentation stage left on the GPU).  Builds the summed-area tables of the silhouettes that
- * VC_EXACT's classifier reads (three kernels, C4: 0.36 ms). */
+ * VC_EXACT's classifier reads (a copy + two kernels, C4: 0.16 ms). */
 VC_EXPORT int vc_set_masks(vc_engine* e, const void* masks, int32_t format);
 /* Undistorted colour images 8UC3 BGR (ColorReconstruction.h:23), uint8[V][H][W][3], HOST memory. */
 VC_EXPORT int vc_set_images(vc_engine* e, const uint8_t* images_bgr);
