@@ -73,8 +73,9 @@ enum vc_mask_format { VC_MASK_BITS = 0, VC_MASK_BGR8 = 1, VC_MASK_BGR8_RAW = 2 /
 
 typedef struct vc_stats {
     double last_carve_ms;          /* CUDA-event time of the last vc_carve (all its kernels) */
-    double last_classify_ms;       /* of which: the two brick-classification kernels (0 for the flat modes); the rest is the per-voxel
-                                      kernel, whose first blocks also run the fill pass on a fresh carve */
+    double last_classify_ms;       /* of which (profiling mode only, else 0): the two brick-classification kernels and, on a fresh carve,
+                                      the blind fill in front of them; the rest is the per-voxel kernel, whose first blocks also run
+                                      the patch pass */
     uint64_t nominal_voxel_views;  /* X*Y*(z_end-z_begin)*V of the last vc_carve */
     uint64_t executed_voxel_views; /* projections actually evaluated, incl. brick corners (0 unless counting was on) */
     uint64_t brick_corner_views;   /* the part of executed_voxel_views spent on brick classification */

@@ -55,3 +55,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inc")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower() or f == "vc_kernels.cuh" and "oracle: vo_pixel" in txt, os.path.join(dp, f)
+
+
+def test_binding_structs_match_the_header(tmp_path):
+    """vc_grid_desc and vc_stats cross the ABI by pointer: the ctypes mirrors must have the header's fields, in its order, at its
+    offsets (gcc compiles the header and prints offsetof / sizeof)."""
+    import subprocess
+    from ar_voxel_project_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "voxcarve.h")).read()
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "voxcarve.h"', 'int main(void) {']
+    mirrors = {"vc_grid_desc": _lib.GridDesc, "vc_stats": _lib.Stats}
+    for cname, mirror in mirrors.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                fields += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+        assert fields == [n for n, _ in mirror._fields_], (cname, fields)
+        for f in fields:
+            prog.append(f'    printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+        prog.append(f'    printf("{cname} %zu\\n", sizeof({cname}));')
+    prog += ['    return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, mirror in mirrors.items():
+        assert int(out[cname]) == ctypes.sizeof(mirror)
+        for n, _ in mirror._fields_:
+            assert int(out[f"{cname}.{n}"]) == getattr(mirror, n).offset, (cname, n)
