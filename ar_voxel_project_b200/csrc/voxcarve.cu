@@ -200,8 +200,9 @@ struct VmmApi {
     CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
     CUresult (*MemGetAllocationPropertiesFromHandle)(CUmemAllocationProp*, CUmemGenericAllocationHandle) = nullptr;
     CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+    CUresult (*DevicePrimaryCtxGetState)(CUdevice, unsigned int*, int*) = nullptr;
 };
-struct VmmBlock { size_t size; CUmemGenericAllocationHandle handle; };
+struct VmmBlock { size_t size; CUmemGenericAllocationHandle handle; unsigned long long access_mask; };  // bit d: device d may read / write it
 static VmmApi g_vmm;
 static std::mutex g_vmm_mutex;
 static std::map<void*, VmmBlock> g_vmm_blocks;
@@ -226,11 +227,14 @@ static bool vmm_load() {  // g_vmm_mutex held
     get("cuMemGetAllocationGranularity", (void**)&g_vmm.MemGetAllocationGranularity);
     get("cuMemGetAllocationPropertiesFromHandle", (void**)&g_vmm.MemGetAllocationPropertiesFromHandle);
     get("cuDeviceGetAttribute", (void**)&g_vmm.DeviceGetAttribute);
+    get("cuDevicePrimaryCtxGetState", (void**)&g_vmm.DevicePrimaryCtxGetState);
     g_vmm.ok = ok;
     return ok;
 }
 
-// compressible memory on `device` (the current one), readable / writable from every device that can reach it; nullptr = not granted
+// compressible memory on `device` (the current one), readable / writable from the devices this process already works on and can
+// reach it from (the other engines of a multi-engine host; a process per GPU maps its own device only); engines that come later
+// are granted access when they first take part in a peer copy (vol_grant_access); nullptr = not granted
 static void* vmm_alloc_compressible(int device, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_vmm_mutex);
     if (!vmm_load()) return nullptr;
@@ -252,25 +256,50 @@ static void* vmm_alloc_compressible(int device, size_t bytes) {
     if (g_vmm.MemAddressReserve(&va, size, 0, 0, 0) != CUDA_SUCCESS) { g_vmm.MemRelease(h); return nullptr; }
     if (g_vmm.MemMap(va, size, 0, h, 0) != CUDA_SUCCESS) { g_vmm.MemAddressFree(va, size); g_vmm.MemRelease(h); return nullptr; }
     std::vector<CUmemAccessDesc> acc;
+    unsigned long long mask = 0;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess) { cudaGetLastError(); n_dev = device + 1; }
-    for (int d = 0; d < n_dev; d++) {  // the halo / gather copies between engines of one process read and write peers' volumes
+    for (int d = 0; d < n_dev && d < 64; d++) {  // the halo / gather copies between engines of one process read and write peers' volumes
         int can = d == device;
-        if (!can && cudaDeviceCanAccessPeer(&can, d, device) != cudaSuccess) { cudaGetLastError(); can = 0; }
+        if (!can) {
+            unsigned int flags = 0;
+            int active = 0;
+            if (g_vmm.DevicePrimaryCtxGetState((CUdevice)d, &flags, &active) != CUDA_SUCCESS || !active) continue;  // not a device of this process (so far)
+            if (cudaDeviceCanAccessPeer(&can, d, device) != cudaSuccess) { cudaGetLastError(); can = 0; }
+        }
         if (!can) continue;
         CUmemAccessDesc a = {};
         a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         a.location.id = d;
         a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
         acc.push_back(a);
+        mask |= 1ull << d;
     }
     if (g_vmm.MemSetAccess(va, size, acc.data(), acc.size()) != CUDA_SUCCESS) {
         CUmemAccessDesc a = {};  // at least the owner
         a.location.type = CU_MEM_LOCATION_TYPE_DEVICE; a.location.id = device; a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        mask = 1ull << device;
         if (g_vmm.MemSetAccess(va, size, &a, 1) != CUDA_SUCCESS) { g_vmm.MemUnmap(va, size); g_vmm.MemAddressFree(va, size); g_vmm.MemRelease(h); return nullptr; }
     }
-    g_vmm_blocks[(void*)va] = VmmBlock{size, h};
+    g_vmm_blocks[(void*)va] = VmmBlock{size, h, mask};
     return (void*)va;
+}
+
+// before a copy between engines: let `device` read / write the volume that holds address `p` (no-op for cudaMalloc / caller memory)
+static void vol_grant_access(const void* p, int device) {
+    if (!p || device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_vmm_mutex);
+    auto it = g_vmm_blocks.upper_bound((void*)p);  // first block that starts beyond p
+    if (it == g_vmm_blocks.begin()) return;
+    --it;
+    if ((const char*)p >= (const char*)it->first + it->second.size || (it->second.access_mask >> device) & 1ull) return;
+    CUmemAccessDesc a = {};
+    a.location.type = CU_MEM_LOCATION_TYPE_DEVICE; a.location.id = device; a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (g_vmm.MemSetAccess((CUdeviceptr)it->first, it->second.size, &a, 1) == CUDA_SUCCESS) it->second.access_mask |= 1ull << device;
+}
+static void grant_peer_access(vc_engine* owner, int device) {  // all of `owner`'s engine-owned volumes
+    vol_grant_access(owner->d_occ_own, device); vol_grant_access(owner->d_seen_own, device);
+    vol_grant_access(owner->d_occ_full_own, device); vol_grant_access(owner->d_seen_full_own, device);
 }
 
 static cudaError_t vol_alloc(vc_engine* e, uint32_t** out, size_t bytes) {
@@ -1908,6 +1937,7 @@ int vc_import_halo(vc_engine* e, int32_t which, const void* d_plane) {
     uint32_t* dst = halo_slot(e, which);
     if (!dst) return fail(e, VC_ERR_ARG, "vc_import_halo: plane %s of slab [%d,%d) lies outside the grid (it is empty by definition, Model.h:119-124)",
                           which == 0 ? "z_begin - 1" : "z_end", e->g.z_begin, e->g.z_end);
+    vol_grant_access(d_plane, e->g.device);  // a neighbour engine's plane in this process (vc_export_halo) may live in memory not yet mapped here
     VC_CUDA(e, cudaMemcpyAsync(dst, d_plane, (size_t)e->plane_words * 4, cudaMemcpyDefault, e->stream));
     valid = true;
     e->have_colors = false;
@@ -1935,6 +1965,7 @@ int vc_exchange_halos_peer(vc_engine** engines, int32_t n) {
     const size_t bytes = (size_t)e0->plane_words * 4;
     for (int i = 0; i + 1 < n; i++) {
         vc_engine *a = es[i], *b = es[i + 1];  // a below b: a's last plane is b's z_begin - 1, b's first plane is a's z_end
+        grant_peer_access(a, b->g.device); grant_peer_access(b, a->g.device);
         if (bind_device(b)) return VC_ERR_CUDA;
         VC_CUDA(b, cudaStreamWaitEvent(b->stream, a->ev_halo, 0));
         VC_CUDA(b, cudaMemcpyAsync(halo_slot(b, 0), a->occ_slab() + a->slab_words - a->plane_words, bytes, cudaMemcpyDefault, b->stream));
@@ -1964,6 +1995,7 @@ int vc_gather_peer(vc_engine** engines, int32_t n, int32_t what) {
         if (rc) return rc;
         for (int k = 0; k < n; k++) {  // direct loads / stores over NVLink instead of staging through the host
             if (es[k]->g.device == e->g.device) continue;
+            grant_peer_access(e, es[k]->g.device);
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, e->g.device, es[k]->g.device) == cudaSuccess && can) {
                 const cudaError_t pe = cudaDeviceEnablePeerAccess(es[k]->g.device, 0);
