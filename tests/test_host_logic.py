@@ -135,3 +135,28 @@ def test_output_buffers_are_never_copied_behind_the_callers_back():
         _host_out_ptr(ro, ok.nbytes, "t")
     with pytest.raises(TypeError):
         _host_out_ptr([0] * 24, ok.nbytes, "t")
+
+
+def test_patch_pass_byte_tricks_match_the_per_brick_definition():
+    """vc_patch4_planes (vc_kernels.cuh) decides for four bricks at once which words the blind fill left wrong: byte k of a 32-bit
+    flag word is skipped iff brick k is carved AND seen (the blind pattern is right) or listed (the work items own it).  The two
+    SWAR expressions are restated here and checked against the per-byte definition for every pair of adjacent flag bytes and a
+    random sample of whole words (carries between bytes are what could go wrong)."""
+    CARVED, SEEN, DECIDED, LISTED = 1, 2, 4, 8
+    rng = np.random.default_rng(3)
+    words = [a | (b << 8) | (c << 16) | (d << 24) for a in range(16) for b in range(16) for c in (0, 5, 15) for d in (0, 3, 15)]
+    words += [int(x) for x in rng.integers(0, 16, size=(4000, 4), dtype=np.uint32) @ np.array([1, 1 << 8, 1 << 16, 1 << 24], dtype=np.uint64)]
+    words += [w | 0xf0f0f0f0 for w in words[:500]]   # high nibbles are unused today: they must not leak into the low bits
+    for f4 in words:
+        f4 &= 0xffffffff
+        cs = f4 & (f4 >> 1) & (CARVED * 0x01010101)
+        skip = cs | ((f4 // LISTED) & 0x01010101)
+        for k in range(4):
+            b = (f4 >> (8 * k)) & 0xff
+            want = ((b & (CARVED | SEEN)) == (CARVED | SEEN)) or bool(b & LISTED)
+            assert ((skip >> (8 * k)) & 1) == int(want), (hex(f4), k)
+            assert (skip >> (8 * k)) & 0xfe == 0
+    # the sentinel for layers beyond the slab is skipped whole
+    sf = DECIDED | CARVED | SEEN
+    f4 = (sf & 0xff) * 0x01010101
+    assert (f4 & (f4 >> 1) & 0x01010101) == 0x01010101
